@@ -1,0 +1,191 @@
+/*
+ * lpd_b200.h — C ABI of the B200 (sm_100a) kernels behind the LPD-Net hot path.
+ *
+ * The reference (qiaozhijian/LPD-Net-Pytorch) has no FFI of its own: its hot path is a chain of
+ * torch ops inside util/lpdnet_model.py, util/PointNetVlad.py, loss/pointnetvlad_loss.py and
+ * evaluate.py.  Every entry point below names the reference call site (file:line, relative to the
+ * reference root) whose arithmetic it replaces.  The Python host modules in
+ * lpd-net-pytorch_b200/ bind these with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All pointers are DEVICE pointers unless the
+ *     name ends in _host.  The caller owns every buffer (inputs, outputs, workspaces).
+ *   - fp32 storage everywhere, row-major, POINT-MAJOR: a feature map is X[rows][C] with
+ *     rows = B*N points and C contiguous.  (The reference is channel-major [B,C,N]; the host
+ *     modules transpose only at the public per-function boundary.)
+ *   - kNN / retrieval indices are int32 and CLOUD-LOCAL (0..N-1) unless stated otherwise.
+ *   - `stream` is a cudaStream_t passed as void*.  All launches are asynchronous on it;
+ *     nothing synchronises, allocates or frees.
+ *   - Return value: LPD_OK (0) or a negative lpd_status.  No exceptions cross the ABI.
+ */
+#ifndef LPD_B200_H
+#define LPD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPD_ABI_VERSION 1
+
+typedef enum lpd_status {
+    LPD_OK = 0,
+    LPD_EINVAL = -1,     /* bad shape / alignment / unsupported parameter            */
+    LPD_EWORKSPACE = -2, /* workspace too small                                       */
+    LPD_ECUDA = -3,      /* a CUDA runtime call or launch failed (see lpd_last_cuda_error) */
+    LPD_EUNSUPPORTED = -4 /* device is not sm_100 or feature not built                */
+} lpd_status;
+
+/* activation selector of the fused epilogues */
+typedef enum lpd_act {
+    LPD_ACT_NONE = 0,
+    LPD_ACT_RELU = 1,      /* F.relu, PointNetVlad.py:156-167, lpdnet_model.py:297-303 */
+    LPD_ACT_LEAKY = 2,     /* nn.LeakyReLU(slope), lpdnet_model.py:24,153             */
+    LPD_ACT_SIGMOID = 3,   /* nn.Sigmoid, PointNetVlad.py:111                          */
+    LPD_ACT_GATE = 4       /* out = aux * sigmoid(v): GatingContext, PointNetVlad.py:111-113 */
+} lpd_act;
+
+/* operand layouts of lpd_gemm */
+#define LPD_A_MK 0 /* A stored [M][K], K contiguous */
+#define LPD_A_KM 1 /* A stored [K][M], M contiguous */
+#define LPD_B_NK 0 /* B stored [N][K], K contiguous (a conv / linear weight [Cout][Cin]) */
+#define LPD_B_KN 1 /* B stored [K][N], N contiguous (NetVLAD cluster / hidden weights)   */
+
+int lpd_abi_version(void);
+const char* lpd_status_str(int status);
+/* text of the last CUDA error seen by this library on the calling thread ("" if none) */
+const char* lpd_last_cuda_error(void);
+/* properties of the current device: SM count, compute capability, opt-in shared memory bytes */
+int lpd_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * Folded BatchNorm (eval mode): scale = gamma / sqrt(var + eps), shift = beta - mean * scale.
+ * Replaces the running-stat branch of every nn.BatchNorm{1,2}d on the path
+ * (lpdnet_model.py:168-191, PointNetVlad.py:33,39,97,215-230).  `bias` (nullable) is the conv /
+ * linear bias that precedes the BN: shift += bias * scale.
+ * ------------------------------------------------------------------------------------------- */
+int lpd_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                const float* bias, float eps, int C, float* scale, float* shift, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched 2-D transpose  in[b][R][C] -> out[b][C][R]   (channel-major <-> point-major)
+ * Replaces the transposes at lpdnet_model.py:212,348 and PointNetVlad.py:46.
+ * ------------------------------------------------------------------------------------------- */
+int lpd_transpose(const float* in, float* out, int batch, int rows, int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * kNN: fused pairwise distance + top-k, the N x N matrix never leaves the SM.
+ * Replaces knn(), lpdnet_model.py:317-326 (matmul, pow/sum, two subtractions, topk).
+ *   x    [B][N][C] point-major, C in {3, 64} (any C <= 64 multiple of 1 is accepted)
+ *   idx  [B][N][k]: k nearest by the CANONICAL order:
+ *          dot_ij = fmaf chain over c = 0..C-1 (acc starts at +0),  xx_j = same chain on (x_j,x_j)
+ *          pd_ij  = ((-xx_j) - (-2*dot_ij)) - xx_i            (fp32, that operation order)
+ *          sorted by pd descending, ties by j ascending.
+ *   idx_i64 != 0 writes int64 (the dtype of the public knn() API), else int32.
+ *   1 <= k <= 32, k <= N.
+ * ------------------------------------------------------------------------------------------- */
+int lpd_knn(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * General fp32 GEMM with fused per-column affine + activation epilogue (CUDA-core FFMA path,
+ * "strict" fp32 arithmetic):
+ *     C[b][m][n] = act( scale[n] * sum_k A[b][m][k] * B[b][k][n] + shift[n] )      (+ aux for GATE)
+ * Replaces every nn.Conv1d / nn.Conv2d 1x1 (+BatchNorm +activation) and nn.Linear / matmul on the
+ * path: lpdnet_model.py:231-232,262,297-305 ; PointNetVlad.py:48,76,104,155-170,209-230.
+ *   scale / shift nullable (=> 1 / 0).  lda/ldb/ldc are leading dimensions in elements,
+ *   stride* are per-batch element strides (0 => operand shared by all batches).
+ *   aux (LPD_ACT_GATE only) has the layout of C.
+ * ------------------------------------------------------------------------------------------- */
+int lpd_gemm(const float* A, int a_layout, int lda, long long strideA,
+             const float* B, int b_layout, int ldb, long long strideB,
+             float* C, int ldc, long long strideC,
+             int M, int N, int K, int batch,
+             const float* scale, const float* shift, int act, float slope, const float* aux,
+             void* stream);
+
+/* column max over rows of each cloud: out[b][c] = max_n x[b][n][c]
+ * (MaxPool2d((num_points,1)) PointNetVlad.py:137,169 ; torch.max(x,2) lpdnet_model.py:300) */
+int lpd_colmax(const float* x, int B, int N, int C, int ldx, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * EdgeConv, neighbour-gather + extremum (exact decomposition of a 1x1 conv over
+ * cat(neighbour, centre) followed by a monotone BN+activation and max over k):
+ *     out[i][c] = act( s[c] * (q[i][c] + ext_m p[j(i,m)][c]) + t[c] ),  ext = max if s[c] >= 0 else min
+ * Replaces get_graph_feature + convDG1/convSN1 + max, lpdnet_model.py:246-250,255-258 (x1, x3),
+ * and with q == NULL the gather-only edges of LPDNetOrign, lpdnet_model.py:104-107.
+ *   p, q: [B*N][ldp / ldq] (C columns used), idx [B][N][k] cloud-local int32.
+ * ------------------------------------------------------------------------------------------- */
+int lpd_edge_gather_ext(const float* p, int ldp, const float* q, int ldq,
+                        const int32_t* idx, int B, int N, int k, int C,
+                        const float* scale, const float* shift, int act, float slope,
+                        float* out, int ldo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * EdgeConv, two chained edge layers fused; the N x k x C edge tensors never touch HBM:
+ *     y1[i][m][:] = act(s1 * (p[j(i,m)][:] + q[i][:]) + t1)        C1 channels
+ *     y2[i][m][:] = act(s2 * (W2 . y1[i][m][:]) + t2)              C2 channels, W2 [C2][C1]
+ *     x1[i][:] = max_m y1[i][m][:]  (optional, x1 may be NULL)     x2[i][:] = max_m y2[i][m][:]
+ * Replaces get_graph_feature + convDG1 + max + convDG2 + max, lpdnet_model.py:246-252 (C1=C2=128)
+ * and get_graph_feature_Origin + convDG1 + convDG2 + max, lpdnet_model.py:98-101 (C1=C2=64).
+ * ------------------------------------------------------------------------------------------- */
+int lpd_edgeconv_dg(const float* p, int ldp, const float* q, int ldq,
+                    const int32_t* idx, int B, int N, int k, int C1, int C2,
+                    const float* s1, const float* t1, const float* w2,
+                    const float* s2, const float* t2, int act, float slope,
+                    float* x1, int ld1, float* x2, int ld2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NetVLAD soft-assignment: a[m][:] = softmax_K( s * (x[m][:] . Wc) + t )
+ * Replaces PointNetVlad.py:48-59 (matmul, BatchNorm1d(K) or cluster_biases, softmax).
+ *   x [M][D], wc [D][K] (the reference's cluster_weights layout), a [M][K], K == 64.
+ * ------------------------------------------------------------------------------------------- */
+int lpd_netvlad_assign(const float* x, int M, int D, const float* wc, const float* scale,
+                       const float* shift, int K, float* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NetVLAD residual + normalisations, in place on the raw aggregate
+ *     vraw[b][d][k] = sum_n a[b][n][k] * x[b][n][d]     (computed with lpd_gemm, A_KM x B_KN)
+ *     v = vraw - (sum_n a[b][n][k]) * wc2[d][k] ; v /= max(||v[:,k]||,1e-12) ; v /= max(||v||,1e-12)
+ * Replaces PointNetVlad.py:61-74.  `asum_ws` is a [B][8][K] float workspace (partial sums over N).
+ * ------------------------------------------------------------------------------------------- */
+int lpd_netvlad_finish(float* vlad, const float* a, const float* wc2, int B, int N, int D, int K,
+                       float* asum_ws, void* stream);
+
+/* deterministic split-K reduce + affine: out[m][n] = scale[n]*sum_s part[s][m][n] + shift[n]
+ * (second half of the 65536->256 hidden projection + bn2, PointNetVlad.py:76-78) */
+int lpd_splitk_reduce(const float* part, int splits, int M, int N, const float* scale,
+                      const float* shift, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Lazy / non-lazy triplet and quadruplet hinge losses, forward and backward in one launch each.
+ * Replaces best_pos_distance / triplet_loss / quadruplet_loss, loss/pointnetvlad_loss.py:6-97.
+ *   q [Bq][1][D], pos [Bq][P][D], neg [Bq][Nn][D], other [Bq][1][D] (other == NULL => triplet)
+ *   flags: bit0 use_min, bit1 lazy, bit2 ignore_zero_loss.
+ *   loss: 1 float.  Gradients (nullable as a group) have the input layouts and are the gradient
+ *   of `loss` scaled by *grad_out (device scalar, nullable => 1).
+ * ------------------------------------------------------------------------------------------- */
+int lpd_quadruplet_loss(const float* q, const float* pos, const float* neg, const float* other,
+                        int Bq, int P, int Nn, int D, float m1, float m2, int flags,
+                        float* loss, float* gq, float* gpos, float* gneg, float* gother,
+                        const float* grad_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Retrieval: exact brute-force k nearest database rows of every query, Euclidean, fp64
+ * difference-form accumulation (the arithmetic of sklearn KDTree on float32 input), ties by
+ * lower database index.  Replaces KDTree(database).query(q, k=25), evaluate.py:168,186-187.
+ *   db [Ndb][D], q [Nq][D], idx [Nq][k] int32 (+ idx_offset added, for sharded databases),
+ *   dist [Nq][k] double (squared distances; nullable).  1 <= k <= 32.  Entries beyond Ndb are -1.
+ *   workspace: device scratch of at least lpd_retrieval_workspace_bytes(Ndb, Nq, k) bytes
+ *   (per-database-split partial lists, merged deterministically).
+ * ------------------------------------------------------------------------------------------- */
+size_t lpd_retrieval_workspace_bytes(int Ndb, int Nq, int k);
+int lpd_retrieval_topk(const float* db, int Ndb, const float* q, int Nq, int D, int k,
+                       int idx_offset, int32_t* idx, double* dist,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPD_B200_H */

@@ -1,0 +1,200 @@
+// Fused pairwise distance + top-k (kNN).  Replaces knn(), reference util/lpdnet_model.py:317-326.
+//
+// One CTA owns 64 query points of one cloud and streams the cloud's N candidate points through
+// shared memory in tiles of 128.  A 64x128 tile of canonical distances is produced by a
+// register-tiled FFMA loop (4x8 per thread), parked in shared memory, and consumed by a
+// warp-resident selection network: every warp keeps the running top-k of 8 query rows as a
+// sorted list spread over its lanes (lane l = l-th best), filters the tile against the current
+// k-th value with one compare per element, and inserts survivors with shuffles.  The N x N
+// distance matrix (64 MiB per cloud in the reference) never exists outside the SM.
+//
+// Canonical arithmetic (the CPU oracle oracle/knn_canonical.c is the same code):
+//   dot_ij = fmaf(x_i[C-1], x_j[C-1], ... fmaf(x_i[0], x_j[0], +0))     ascending c
+//   xx_j   = the same chain on (x_j, x_j)
+//   pd_ij  = ((-xx_j) - (-2 * dot_ij)) - xx_i
+//   order  = pd descending, then j ascending.
+// Zero padding of the channel axis leaves the chain bit-identical (fmaf(0,0,a) == a).
+#include "common.cuh"
+#include <limits.h>
+
+namespace lpd {
+
+constexpr int KNN_QT = 64;        // query rows per CTA
+constexpr int KNN_CT = 128;       // candidate columns per tile
+constexpr int KNN_THREADS = 256;  // 8 warps
+constexpr int KNN_RPW = KNN_QT / (KNN_THREADS / 32);  // rows per warp = 8
+
+// global point-major [rows][C]  ->  shared channel-major dst[CP][ROWS], zero padded
+template <int CP, int ROWS>
+__device__ __forceinline__ void knn_load_tile(const float* __restrict__ xb, int row0, int N, int C,
+                                              float* __restrict__ dst, int tid) {
+    if ((C & 3) == 0) {
+        constexpr int G = CP / 4;
+        for (int e = tid; e < ROWS * G; e += KNN_THREADS) {
+            const int p = e % ROWS, g = e / ROWS;
+            const int row = row0 + p;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < N && 4 * g < C) v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * C + 4 * g));
+            dst[(4 * g + 0) * ROWS + p] = v.x;
+            dst[(4 * g + 1) * ROWS + p] = v.y;
+            dst[(4 * g + 2) * ROWS + p] = v.z;
+            dst[(4 * g + 3) * ROWS + p] = v.w;
+        }
+    } else {
+        for (int e = tid; e < ROWS * CP; e += KNN_THREADS) {
+            const int p = e % ROWS, c = e / ROWS;
+            const int row = row0 + p;
+            float v = 0.f;
+            if (row < N && c < C) v = __ldg(xb + (size_t)row * C + c);
+            dst[c * ROWS + p] = v;
+        }
+    }
+}
+
+template <int CP, int ROWS>
+__device__ __forceinline__ float knn_sqnorm(const float* __restrict__ t, int p) {
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+        const float v = t[c * ROWS + p];
+        acc = __fmaf_rn(v, v, acc);
+    }
+    return acc;
+}
+
+template <int CP>
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ idx_out, int idx_i64) {
+    extern __shared__ __align__(16) float smem[];
+    float* Qs = smem;                      // [CP][QT]
+    float* Cs = Qs + CP * KNN_QT;          // [CP][CT]
+    float* Ds = Cs + CP * KNN_CT;          // [QT][CT]
+    float* xxq = Ds + KNN_QT * KNN_CT;     // [QT]
+    float* xxc = xxq + KNN_QT;             // [CT]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 thread grid: 4 rows x 8 cols each
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * KNN_QT;
+    const float* xb = x + (size_t)b * N * C;
+
+    knn_load_tile<CP, KNN_QT>(xb, q0, N, C, Qs, tid);
+
+    float lv[KNN_RPW];
+    int li[KNN_RPW];
+#pragma unroll
+    for (int r = 0; r < KNN_RPW; ++r) { lv[r] = -INFINITY; li[r] = INT_MAX; }
+
+    for (int c0 = 0; c0 < N; c0 += KNN_CT) {
+        knn_load_tile<CP, KNN_CT>(xb, c0, N, C, Cs, tid);
+        __syncthreads();  // S1: tile visible; previous selection finished before Ds is rewritten
+
+        if (tid < KNN_CT) xxc[tid] = knn_sqnorm<CP, KNN_CT>(Cs, tid);
+        else if (c0 == 0 && tid < KNN_CT + KNN_QT) xxq[tid - KNN_CT] = knn_sqnorm<CP, KNN_QT>(Qs, tid - KNN_CT);
+
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            const float4 a = *reinterpret_cast<const float4*>(Qs + c * KNN_QT + ty * 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(Cs + c * KNN_CT + tx * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(Cs + c * KNN_CT + 64 + tx * 4);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();  // S2: norms visible, everyone done reading Cs
+
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = ty * 4 + i;
+            const float xi = xxq[row];
+            float pd[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = (j < 4) ? (tx * 4 + j) : (64 + tx * 4 + (j - 4));
+                const float t = -2.0f * acc[i][j];
+                const float u = __fsub_rn(-xxc[col], t);
+                pd[j] = __fsub_rn(u, xi);
+            }
+            *reinterpret_cast<float4*>(Ds + row * KNN_CT + tx * 4) = make_float4(pd[0], pd[1], pd[2], pd[3]);
+            *reinterpret_cast<float4*>(Ds + row * KNN_CT + 64 + tx * 4) = make_float4(pd[4], pd[5], pd[6], pd[7]);
+        }
+        __syncthreads();  // S3: distance tile complete
+
+        // ---- selection: warp w owns rows w*8 .. w*8+7 ----
+#pragma unroll
+        for (int r = 0; r < KNN_RPW; ++r) {
+            const int row = warp * KNN_RPW + r;
+            float tv = __shfl_sync(kFull, lv[r], k - 1);
+            int ti = __shfl_sync(kFull, li[r], k - 1);
+#pragma unroll
+            for (int t = 0; t < KNN_CT / 32; ++t) {
+                const float v = Ds[row * KNN_CT + t * 32 + lane];
+                const int j = c0 + t * 32 + lane;
+                const bool pass = (j < N) && (v > tv || (v == tv && j < ti));
+                unsigned mask = __ballot_sync(kFull, pass);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float cv = __shfl_sync(kFull, v, src);
+                    const int cj = __shfl_sync(kFull, j, src);
+                    const bool better = (lv[r] > cv) || (lv[r] == cv && li[r] < cj);
+                    const int pos = __popc(__ballot_sync(kFull, better));
+                    if (pos < k) {  // warp-uniform
+                        const float upv = __shfl_up_sync(kFull, lv[r], 1);
+                        const int upi = __shfl_up_sync(kFull, li[r], 1);
+                        if (lane < k) {
+                            if (lane > pos) { lv[r] = upv; li[r] = upi; }
+                            else if (lane == pos) { lv[r] = cv; li[r] = cj; }
+                        }
+                        tv = __shfl_sync(kFull, lv[r], k - 1);
+                        ti = __shfl_sync(kFull, li[r], k - 1);
+                    }
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < KNN_RPW; ++r) {
+        const int row = q0 + warp * KNN_RPW + r;
+        if (row < N && lane < k) {
+            const size_t o = ((size_t)b * N + row) * k + lane;
+            if (idx_i64) reinterpret_cast<long long*>(idx_out)[o] = li[r];
+            else reinterpret_cast<int*>(idx_out)[o] = li[r];
+        }
+    }
+}
+
+template <int CP>
+static int knn_launch(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, cudaStream_t st) {
+    const size_t smem = (size_t)(CP * (KNN_QT + KNN_CT) + KNN_QT * KNN_CT + KNN_QT + KNN_CT) * sizeof(float);
+    LPD_CUDA_CHECK(allow_smem(knn_kernel<CP>, smem));
+    dim3 grid(ceil_div(N, KNN_QT), B);
+    knn_kernel<CP><<<grid, KNN_THREADS, smem, st>>>(x, N, C, k, idx, idx_i64);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+}  // namespace lpd
+
+extern "C" int lpd_knn(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(x != nullptr && idx != nullptr);
+    LPD_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && C >= 1 && C <= 64);
+    LPD_REQUIRE(k >= 1 && k <= 32 && k <= N);
+    cudaStream_t st = as_stream(stream);
+    if (C <= 4) return knn_launch<4>(x, B, N, C, k, idx, idx_i64, st);
+    if (C <= 8) return knn_launch<8>(x, B, N, C, k, idx, idx_i64, st);
+    if (C <= 16) return knn_launch<16>(x, B, N, C, k, idx, idx_i64, st);
+    if (C <= 32) return knn_launch<32>(x, B, N, C, k, idx, idx_i64, st);
+    return knn_launch<64>(x, B, N, C, k, idx, idx_i64, st);
+}

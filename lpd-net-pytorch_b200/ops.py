@@ -1,0 +1,166 @@
+"""Tensor-level wrappers over the C ABI: torch supplies device memory and the stream, nothing else.
+
+Every function takes CUDA float32 (or int32) tensors, allocates its outputs with torch.empty and
+launches on torch's current stream.  Feature maps are POINT-MAJOR [rows, C] (see include/lpd_b200.h).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GATE, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, A_KM, A_MK, B_KN, B_NK)
+
+__all__ = ["bn_fold", "transpose", "knn", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
+           "netvlad_assign", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
+           "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ACT_SIGMOID", "ACT_GATE", "A_MK", "A_KM", "B_NK", "B_KN"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.LpdError(f"{name} must be a CUDA tensor: the lpd_b200 kernels have no CPU path")
+    if t.dtype != torch.float32:
+        raise _lib.LpdError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def bn_fold(gamma, beta, mean, var, eps: float, bias=None):
+    """(scale, shift) of an eval-mode BatchNorm, optionally absorbing a preceding conv bias."""
+    lib = _lib.load()
+    C = mean.numel()
+    out = torch.empty(2, C, device=mean.device, dtype=torch.float32)
+    _lib.check(lib.lpd_bn_fold(_p(gamma), _p(beta), _p(mean), _p(var), _p(bias), float(eps), C,
+                               out[0].data_ptr(), out[1].data_ptr(), _stream()), "lpd_bn_fold")
+    return out[0], out[1]
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """[b, R, C] -> [b, C, R] (contiguous)."""
+    lib = _lib.load()
+    x = _f32(x, "x").contiguous()
+    b, R, Cc = x.shape
+    out = torch.empty(b, Cc, R, device=x.device, dtype=torch.float32)
+    _lib.check(lib.lpd_transpose(x.data_ptr(), out.data_ptr(), b, R, Cc, _stream()), "lpd_transpose")
+    return out
+
+
+def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
+    """x_pm [B, N, C] point-major -> idx [B, N, k] (int32, or int64 for the public API)."""
+    lib = _lib.load()
+    x_pm = _f32(x_pm, "x").contiguous()
+    B, N, Cc = x_pm.shape
+    idx = torch.empty(B, N, k, device=x_pm.device, dtype=torch.int64 if int64 else torch.int32)
+    _lib.check(lib.lpd_knn(x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64), _stream()), "lpd_knn")
+    return idx
+
+
+def gemm(A, B, *, a_layout=A_MK, b_layout=B_NK, M, N, K, lda=None, ldb=None, out=None, ldc=None,
+         batch=1, strideA=0, strideB=0, strideC=0, scale=None, shift=None, act=ACT_NONE, slope=0.0, aux=None):
+    """out[b][m][n] = act(scale[n] * sum_k A[b][m][k] B[b][k][n] + shift[n]); see lpd_gemm."""
+    lib = _lib.load()
+    _f32(A, "A"), _f32(B, "B")
+    if lda is None:
+        lda = K if a_layout == A_MK else M
+    if ldb is None:
+        ldb = K if b_layout == B_NK else N
+    if out is None:
+        ldc = N
+        out = torch.empty((batch, M, N) if batch > 1 else (M, N), device=A.device, dtype=torch.float32)
+        if batch > 1:
+            strideC = M * N
+    elif ldc is None:
+        ldc = out.stride(-2)
+    _lib.check(lib.lpd_gemm(A.data_ptr(), a_layout, lda, strideA, B.data_ptr(), b_layout, ldb, strideB,
+                            out.data_ptr(), ldc, strideC, M, N, K, batch, _p(scale), _p(shift), act, float(slope),
+                            _p(aux), _stream()), "lpd_gemm")
+    return out
+
+
+def colmax(x: torch.Tensor, B: int, N: int, C: int, ldx: int | None = None) -> torch.Tensor:
+    lib = _lib.load()
+    _f32(x, "x")
+    out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    _lib.check(lib.lpd_colmax(x.data_ptr(), B, N, C, C if ldx is None else ldx, out.data_ptr(), _stream()), "lpd_colmax")
+    return out
+
+
+def edge_gather_ext(p, ldp, q, ldq, idx, B, N, k, C, scale, shift, act, slope, out, ldo):
+    lib = _lib.load()
+    _lib.check(lib.lpd_edge_gather_ext(p.data_ptr(), ldp, _p(q), ldq, idx.data_ptr(), B, N, k, C, _p(scale), _p(shift),
+                                       act, float(slope), out.data_ptr(), ldo, _stream()), "lpd_edge_gather_ext")
+    return out
+
+
+def edgeconv_dg(p, ldp, q, ldq, idx, B, N, k, C1, C2, s1, t1, w2, s2, t2, act, slope, x1, ld1, x2, ld2):
+    lib = _lib.load()
+    _lib.check(lib.lpd_edgeconv_dg(p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), B, N, k, C1, C2,
+                                   s1.data_ptr(), t1.data_ptr(), w2.data_ptr(), s2.data_ptr(), t2.data_ptr(),
+                                   act, float(slope), _p(x1), ld1, x2.data_ptr(), ld2, _stream()), "lpd_edgeconv_dg")
+    return x1, x2
+
+
+def netvlad_assign(x, M, D, wc, scale, shift, K=64, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(M, K, device=x.device, dtype=torch.float32)
+    _lib.check(lib.lpd_netvlad_assign(x.data_ptr(), M, D, wc.data_ptr(), _p(scale), _p(shift), K, out.data_ptr(),
+                                      _stream()), "lpd_netvlad_assign")
+    return out
+
+
+def netvlad_finish(vlad, a, wc2, B, N, D, K=64):
+    """in place on vlad [B, D, K]; returns it viewed as [B, D*K]."""
+    lib = _lib.load()
+    ws = torch.empty(B * 8 * K, device=vlad.device, dtype=torch.float32)
+    _lib.check(lib.lpd_netvlad_finish(vlad.data_ptr(), a.data_ptr(), wc2.data_ptr(), B, N, D, K, ws.data_ptr(),
+                                      _stream()), "lpd_netvlad_finish")
+    return vlad.view(B, D * K)
+
+
+def splitk_reduce(part, splits, M, N, scale=None, shift=None):
+    lib = _lib.load()
+    out = torch.empty(M, N, device=part.device, dtype=torch.float32)
+    _lib.check(lib.lpd_splitk_reduce(part.data_ptr(), splits, M, N, _p(scale), _p(shift), out.data_ptr(), _stream()),
+               "lpd_splitk_reduce")
+    return out
+
+
+def quadruplet_loss(q, pos, neg, other, m1, m2, use_min, lazy, ignore_zero_loss, need_grad=False, grad_out=None):
+    """Returns loss [1] and, if need_grad, (gq, gpos, gneg, gother)."""
+    lib = _lib.load()
+    q, pos, neg = _f32(q, "q").contiguous(), _f32(pos, "pos").contiguous(), _f32(neg, "neg").contiguous()
+    other = None if other is None else _f32(other, "other").contiguous()
+    Bq, P, D = pos.shape
+    Nn = neg.shape[1]
+    flags = int(bool(use_min)) | (int(bool(lazy)) << 1) | (int(bool(ignore_zero_loss)) << 2)
+    loss = torch.empty(1, device=q.device, dtype=torch.float32)
+    grads = (None, None, None, None)
+    if need_grad:
+        grads = (torch.empty_like(q), torch.empty_like(pos), torch.empty_like(neg),
+                 None if other is None else torch.empty_like(other))
+    _lib.check(lib.lpd_quadruplet_loss(q.data_ptr(), pos.data_ptr(), neg.data_ptr(), _p(other), Bq, P, Nn, D,
+                                       float(m1), float(m2), flags, loss.data_ptr(), _p(grads[0]), _p(grads[1]),
+                                       _p(grads[2]), _p(grads[3]), _p(grad_out), _stream()), "lpd_quadruplet_loss")
+    return (loss, grads) if need_grad else loss
+
+
+def retrieval_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_offset: int = 0, want_dist: bool = True):
+    """db [Ndb, D], q [Nq, D] -> (idx int32 [Nq, k], squared dist float64 [Nq, k] or None)."""
+    lib = _lib.load()
+    db, q = _f32(db, "db").contiguous(), _f32(q, "q").contiguous()
+    Ndb, D = db.shape
+    Nq = q.shape[0]
+    idx = torch.empty(Nq, k, device=db.device, dtype=torch.int32)
+    dist = torch.empty(Nq, k, device=db.device, dtype=torch.float64) if want_dist else None
+    ws_bytes = lib.lpd_retrieval_workspace_bytes(Ndb, Nq, k)
+    ws = torch.empty((ws_bytes + 7) // 8, device=db.device, dtype=torch.float64)
+    _lib.check(lib.lpd_retrieval_topk(db.data_ptr(), Ndb, q.data_ptr(), Nq, D, k, idx_offset, idx.data_ptr(), _p(dist),
+                                      ws.data_ptr(), ws.numel() * 8, _stream()), "lpd_retrieval_topk")
+    return idx, dist

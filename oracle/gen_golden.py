@@ -1,0 +1,195 @@
+"""CPU ORACLE — TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the UNMODIFIED
+reference (imported from /root/reference, which exists only in the authoring container) on the seeded
+synthetic inputs of lpdnet_b200.synth.  Run:  python -m oracle.gen_golden [case ...]
+
+The reference has no tests or golden vectors of its own, so these files are the pins:
+tests/test_oracle_vs_golden.py checks the CPU oracle against them (CPU, no GPU needed) and the -m gpu
+tests check the CUDA path against both.
+
+How the reference is imported without touching it:
+  * util/lpdnet_model.py hard-codes torch.device('cuda') (:123,:307,:338); the module-global `torch` of that
+    module is replaced by a proxy whose .device(...) returns cpu and which forwards everything else;
+  * evaluate.py cannot be imported (it imports util.initPara, which parses argv / inits NVML / creates dirs),
+    so get_recall (:162-206) is extracted from its AST and exec'd with np, KDTree and recall_num=25.
+"""
+from __future__ import annotations
+
+import ast
+import hashlib
+import os
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path(os.environ.get("LPD_REFERENCE", "/root/reference"))
+GOLDEN = ROOT / "tests" / "golden"
+sys.path.insert(0, str(ROOT))
+sys.dont_write_bytecode = True
+
+from lpdnet_b200 import synth  # noqa: E402
+
+
+def import_reference():
+    if not REF.exists():
+        raise SystemExit(f"{REF} not found: golden vectors can only be generated in the authoring container")
+    sys.path.insert(0, str(REF))
+    import util.lpdnet_model as L  # noqa
+
+    class _Proxy(types.ModuleType):
+        def __getattr__(self, n):
+            return getattr(torch, n)
+
+        def device(self, *a, **k):
+            return torch.device("cpu")
+
+    L.torch = _Proxy("torch_proxy")
+    import util.PointNetVlad as PNV  # noqa
+    import loss.pointnetvlad_loss as RL  # noqa
+    return L, PNV, RL
+
+
+def extract_get_recall():
+    from sklearn.neighbors import KDTree
+    tree = ast.parse((REF / "evaluate.py").read_text())
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_recall")
+    ns = {"np": np, "KDTree": KDTree, "recall_num": 25}
+    exec(compile(ast.Module([node], []), "evaluate.py", "exec"), ns)
+    return ns["get_recall"]
+
+
+def sha(t) -> str:
+    a = t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def sd_digest(sd) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].numpy()).tobytes())
+    return h.hexdigest()
+
+
+def save(name, **arrays):
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLDEN / f"{name}.npz", **arrays)
+    size = (GOLDEN / f"{name}.npz").stat().st_size
+    print(f"  wrote tests/golden/{name}.npz ({size / 1024:.1f} KiB)")
+
+
+# ----------------------------------------------------------------------------------------------
+def case_knn(L, PNV, RL):
+    """reference knn() (torch matmul + topk) on xyz clouds and on 64-d features, incl. adversarial ties"""
+    torch.manual_seed(0)
+    x = synth.clouds(2, 1024, seed=1234)[:, 0].transpose(2, 1).contiguous()          # [2, 3, 1024]
+    idx = L.knn(x, 20)
+    g = torch.Generator().manual_seed(99)
+    f = torch.nn.functional.leaky_relu(torch.randn(2, 64, 512, generator=g), 0.01)    # [2, 64, 512]
+    idf = L.knn(f, 20)
+    # integer lattice: masses of exact ties; 1 % exact duplicates
+    lat = torch.stack(torch.meshgrid(torch.arange(8.), torch.arange(8.), torch.arange(8.), indexing="ij"), 0).reshape(1, 3, 512)
+    idl = L.knn(lat, 20)
+    save("knn", xyz_sha=sha(x), xyz_idx=idx.numpy().astype(np.int16), feat_sha=sha(f), feat_idx=idf.numpy().astype(np.int16),
+         lattice_idx=idl.numpy().astype(np.int16))
+
+
+def _model_case(PNV, name, featnet, B, N, train=False, k=None, **kw):
+    torch.manual_seed(1234)
+    model = PNV.PointNetVlad(num_points=N, featnet=featnet, emb_dims=1024, **kw)
+    sd = synth.synthetic_state_dict(model)
+    model.load_state_dict(sd)
+    if k is not None:
+        model.emb_nn.k = k
+    model.train(train)
+    x = synth.clouds(B, N)
+    with torch.no_grad():
+        out = model(x)
+    extra = {}
+    if train:
+        # running statistics after one train-mode forward (momentum 0.1, unbiased variance)
+        after = model.state_dict()
+        for key in ("net_vlad.bn2.running_mean", "net_vlad.bn2.running_var", "net_vlad.bn1.running_mean"):
+            extra["after." + key] = after[key].numpy()
+    save(name, out=out.numpy(), x_sha=sha(x), sd_sha=sd_digest(sd), keys=np.array(sorted(sd.keys())),
+         shapes=np.array([str(tuple(sd[k_].shape)) for k_ in sorted(sd.keys())]), **extra)
+
+
+def case_c1_pointnet(L, PNV, RL):
+    _model_case(PNV, "c1_pointnet_eval", "pointnet", 2, 4096)
+    _model_case(PNV, "c1_pointnet_train", "pointnet", 8, 1024, train=True)
+    _model_case(PNV, "c1_pointnet_ft_eval", "pointnet", 2, 1024, feature_transform=True)
+
+
+def case_c2_lpdnet(L, PNV, RL):
+    _model_case(PNV, "c2_lpdnet_eval", "lpdnet", 4, 4096)
+    _model_case(PNV, "c2_lpdnet_eval_small", "lpdnet", 2, 1024)
+    _model_case(PNV, "c2_lpdnet_tnets_eval", "lpdnet", 2, 1024, feature_transform=True, xyz_trans=True)
+    _model_case(PNV, "c2_lpdnetorigin_eval", "lpdnetorigin", 2, 4096)
+    _model_case(PNV, "c5_lpdnet_k32_eval", "lpdnet", 1, 2048, k=32)
+    _model_case(PNV, "c3_lpdnet_train_small", "lpdnet", 8, 1024, train=True)
+
+
+def case_loss(L, PNV, RL):
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    for Bq, P, Nn, D in ((2, 2, 18, 256), (3, 1, 2, 48), (5, 4, 7, 40)):
+        tag = f"{Bq}_{P}_{Nn}"
+        sc = (256.0 / D) ** 0.5
+        base = torch.randn(Bq, 1, D, generator=g) * 0.05 * sc
+        q = base.clone()
+        pos = base + torch.randn(Bq, P, D, generator=g) * 0.02 * sc
+        neg = base + torch.randn(Bq, Nn, D, generator=g) * 0.03 * sc
+        other = base + torch.randn(Bq, 1, D, generator=g) * 0.012 * sc
+        for t, name in ((q, "q"), (pos, "pos"), (neg, "neg"), (other, "other")):
+            out[f"{tag}.{name}"] = t.numpy()
+        for use_min in (False, True):
+            for lazy in (False, True):
+                for ign in (False, True):
+                    ft = f"{tag}.{int(use_min)}{int(lazy)}{int(ign)}"
+                    ins = [t.clone().requires_grad_(True) for t in (q, pos, neg, other)]
+                    lq = RL.quadruplet_loss(*ins, 0.5, 0.2, use_min=use_min, lazy=lazy, ignore_zero_loss=ign)
+                    lq.backward()
+                    out[ft + ".quad"] = lq.detach().numpy()
+                    for t, name in zip(ins, ("gq", "gpos", "gneg", "gother")):
+                        out[f"{ft}.quad.{name}"] = t.grad.numpy()
+                    ins = [t.clone().requires_grad_(True) for t in (q, pos, neg)]
+                    lt = RL.triplet_loss(*ins, 0.5, use_min=use_min, lazy=lazy, ignore_zero_loss=ign)
+                    lt.backward()
+                    out[ft + ".trip"] = lt.detach().numpy()
+                    for t, name in zip(ins, ("gq", "gpos", "gneg")):
+                        out[f"{ft}.trip.{name}"] = t.grad.numpy()
+    save("loss", **out)
+
+
+def case_recall(L, PNV, RL):
+    get_recall = extract_get_recall()
+    DB, Q, SETS = synth.descriptor_database()
+    runs = len(DB)
+    rec, one, sim_n, sim_sum = [], [], [], []
+    for m in range(runs):
+        for n in range(runs):
+            if m == n:
+                continue
+            r, sims, op = get_recall(m, n, DB, Q, SETS)
+            rec.append(r)
+            one.append(op)
+            sim_n.append(len(sims))
+            sim_sum.append(float(np.sum(sims)))
+    rec = np.asarray(rec)
+    print(f"  recall@1 mean {rec[:, 0].mean():.2f} %, recall@1% mean {np.mean(one):.2f} %")
+    save("recall", recall=rec, one_percent=np.asarray(one), sim_count=np.asarray(sim_n), sim_sum=np.asarray(sim_sum),
+         db0_sha=sha(DB[0]), q0_sha=sha(Q[0]))
+
+
+CASES = {"knn": case_knn, "c1": case_c1_pointnet, "c2": case_c2_lpdnet, "loss": case_loss, "recall": case_recall}
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    ref = import_reference()
+    for c in (sys.argv[1:] or list(CASES)):
+        print(f"[gen_golden] {c}")
+        CASES[c](*ref)

@@ -1,0 +1,154 @@
+"""Pins the CPU oracle (oracle/) against golden vectors produced by the REAL reference
+(oracle/gen_golden.py, run in the authoring container).  CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from lpdnet_b200 import synth
+from oracle import knn_canonical, loss_numpy, model_numpy, recall_numpy
+
+
+def sha(a):
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def canonical_pd(x_pm):
+    """fp64 -||xi-xj||^2 for the tie-aware comparison"""
+    x = x_pm.astype(np.float64)
+    g = x @ x.T
+    n = (x * x).sum(1)
+    return -(n[:, None] + n[None, :] - 2 * g)
+
+
+def assert_knn_equivalent(x_pm, idx_a, idx_b, k, ulps=8):
+    """Rows must hold the same neighbour SET, or differ only in candidates whose distance is within a few
+    ulp of the k-th distance (the reference's SGEMM order / topk tie order are unspecified)."""
+    B = x_pm.shape[0]
+    bad = 0
+    for b in range(B):
+        pd = None
+        for i in range(x_pm.shape[1]):
+            sa, sb = set(idx_a[b, i].tolist()), set(idx_b[b, i].tolist())
+            if sa == sb:
+                continue
+            if pd is None:
+                pd = canonical_pd(x_pm[b])
+            kth = np.sort(pd[i])[::-1][k - 1]
+            scale = np.abs(x_pm[b]).max() ** 2 * x_pm.shape[2]
+            tol = ulps * np.finfo(np.float32).eps * max(scale, 1e-30)
+            for j in sa ^ sb:
+                assert abs(pd[i, j] - kth) <= tol, f"cloud {b} row {i}: contested neighbour {j} is not a near-tie"
+            bad += 1
+    return bad
+
+
+def test_canonical_knn_matches_reference_knn(golden):
+    g = golden("knn")
+    x = synth.clouds(2, 1024)[:, 0].transpose(2, 1).contiguous()
+    assert sha(x) == str(g["xyz_sha"])
+    x_pm = x.transpose(2, 1).contiguous().numpy()
+    idx = knn_canonical(x_pm, 20)
+    differing = assert_knn_equivalent(x_pm, idx, g["xyz_idx"].astype(np.int64), 20)
+    assert differing <= 8  # a handful of <=few-ulp near ties out of 2048 rows
+
+    gen = torch.Generator().manual_seed(99)
+    f = torch.nn.functional.leaky_relu(torch.randn(2, 64, 512, generator=gen), 0.01)
+    assert sha(f) == str(g["feat_sha"])
+    f_pm = f.transpose(2, 1).contiguous().numpy()
+    idf = knn_canonical(f_pm, 20)
+    assert assert_knn_equivalent(f_pm, idf, g["feat_idx"].astype(np.int64), 20) <= 4
+    # self is the nearest neighbour and the list is sorted by distance
+    assert (idx[:, :, 0] == np.arange(1024)[None]).all()
+
+
+def test_canonical_knn_tie_break_is_lowest_index():
+    lat = np.stack(np.meshgrid(np.arange(8.), np.arange(8.), np.arange(8.), indexing="ij"), 0).reshape(3, 512).T
+    idx, pd = knn_canonical(lat[None].astype(np.float32), 20, return_pd=True)
+    d = -pd[0]
+    assert (np.diff(d, axis=1) >= 0).all()
+    # within equal distances indices ascend
+    same = np.diff(d, axis=1) == 0
+    assert (np.diff(idx[0], axis=1)[same] > 0).all()
+    # exact: integer lattice distances are integers
+    assert np.array_equal(d, np.round(d))
+
+
+@pytest.mark.parametrize("name,featnet,B,N,kw", [
+    ("c1_pointnet_eval", "pointnet", 2, 4096, {}),
+    ("c1_pointnet_ft_eval", "pointnet", 2, 1024, {"feature_transform": True}),
+    ("c2_lpdnet_eval_small", "lpdnet", 2, 1024, {}),
+    ("c2_lpdnet_tnets_eval", "lpdnet", 2, 1024, {}),
+    ("c2_lpdnetorigin_eval", "lpdnetorigin", 2, 4096, {}),
+    ("c5_lpdnet_k32_eval", "lpdnet", 1, 2048, {"k": 32}),
+    ("c2_lpdnet_eval", "lpdnet", 4, 4096, {}),
+])
+def test_model_oracle_matches_reference_eval(golden, name, featnet, B, N, kw):
+    g = golden(name)
+    shapes = {k: eval(s) for k, s in zip(g["keys"].tolist(), g["shapes"].tolist())}
+    sd = synth.fill_state_dict(shapes)
+    x = synth.clouds(B, N)
+    assert sha(x) == str(g["x_sha"])
+    out = model_numpy.pointnetvlad_forward(sd, x.numpy(), featnet=featnet, train=False, **kw)
+    err = np.abs(out - g["out"]).max()
+    assert err < 2e-5, f"{name}: max-abs {err:.3e}"
+
+
+@pytest.mark.parametrize("name,featnet,B,N", [
+    ("c1_pointnet_train", "pointnet", 8, 1024),
+    ("c3_lpdnet_train_small", "lpdnet", 8, 1024),
+])
+def test_model_oracle_matches_reference_train_mode(golden, name, featnet, B, N):
+    g = golden(name)
+    shapes = {k: eval(s) for k, s in zip(g["keys"].tolist(), g["shapes"].tolist())}
+    sd = synth.fill_state_dict(shapes)
+    x = synth.clouds(B, N)
+    out = model_numpy.pointnetvlad_forward(sd, x.numpy(), featnet=featnet, train=True)
+    # the last BatchNorm1d normalises over only B=8 samples and amplifies upstream rounding
+    err = np.abs(out - g["out"]).max()
+    assert err < 5e-4, f"{name}: max-abs {err:.3e}"
+
+
+def test_loss_oracle_matches_reference(golden):
+    g = golden("loss")
+    for tag in ("2_2_18", "3_1_2", "5_4_7"):
+        q, pos, neg, other = (g[f"{tag}.{n}"] for n in ("q", "pos", "neg", "other"))
+        for um in (0, 1):
+            for lz in (0, 1):
+                for ig in (0, 1):
+                    ft = f"{tag}.{um}{lz}{ig}"
+                    lq = loss_numpy.quadruplet_loss(q, pos, neg, other, 0.5, 0.2, bool(um), bool(lz), bool(ig))
+                    lt = loss_numpy.triplet_loss(q, pos, neg, 0.5, bool(um), bool(lz), bool(ig))
+                    assert abs(lq - g[ft + ".quad"]) <= 1e-5 * abs(g[ft + ".quad"])
+                    assert abs(lt - g[ft + ".trip"]) <= 1e-5 * abs(g[ft + ".trip"])
+                    grads = loss_numpy.quadruplet_loss_grad(q, pos, neg, other, 0.5, 0.2, bool(um), bool(lz), bool(ig))
+                    for a, n in zip(grads, ("gq", "gpos", "gneg", "gother")):
+                        ref = g[f"{ft}.quad.{n}"]
+                        assert np.abs(a - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), (ft, n)
+                    grads = loss_numpy.quadruplet_loss_grad(q, pos, neg, None, 0.5, 0.2, bool(um), bool(lz), bool(ig))
+                    for a, n in zip(grads[:3], ("gq", "gpos", "gneg")):
+                        ref = g[f"{ft}.trip.{n}"]
+                        assert np.abs(a - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), (ft, n)
+
+
+def test_recall_oracle_matches_reference_kdtree(golden):
+    g = golden("recall")
+    DB, Q, SETS = synth.descriptor_database()
+    assert sha(DB[0]) == str(g["db0_sha"]) and sha(Q[0]) == str(g["q0_sha"])
+    runs = len(DB)
+    p = 0
+    # every 7th ordered pair keeps the CPU suite short; the GPU suite checks all 506
+    for m in range(runs):
+        for n in range(runs):
+            if m == n:
+                continue
+            if p % 7 == 0:
+                r, sims, one = recall_numpy.get_recall(m, n, DB, Q, SETS)
+                assert np.array_equal(r, g["recall"][p]), (m, n)
+                assert one == g["one_percent"][p]
+                assert len(sims) == g["sim_count"][p]
+                assert abs(float(np.sum(sims)) - g["sim_sum"][p]) < 1e-4
+            p += 1
+    assert 50.0 < g["recall"][:, 0].mean() < 95.0  # the fixture is not a trivial 100 % identity check
