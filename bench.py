@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — LPD-Net eval embedding throughput (BASELINE.json config C2) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores (oracle port)
+
+One "step" = one pass of the hot path (LPDNet featnet + NetVLAD, eval mode) over one batch of 64 synthetic
+4096-point submaps per GPU.  Batch sharding only — no data-path collective ("scaling": "weak").
+`value`  = submaps/s with inputs already resident in HBM (CUDA events, max over ranks).
+`e2e`    = the same metric through the public bulk-embedding API (evaluate.get_latent_vectors) from pinned HOST
+           memory, H2D of every batch and D2H of every descriptor block inside the timed region.
+`roofline` = the dominant kernel of the step, timed live with CUDA events around its launches.
+`cpu_baseline` = the CPU oracle (a numpy / C restatement of the reference's as-written algorithm) on the box's cores,
+           on a bounded sample of the same workload.  The reference itself is Python + torch and lives only in the
+           authoring container (/root/reference), so kind == "port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "LPD-Net eval embedding throughput (featnet=lpdnet, 4096 pts, k=20, NetVLAD K=64 D=1024 -> 256)"
+UNIT = "submaps/s"
+BATCH, NPTS, KNN = 64, 4096, 20
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# algorithmic work per launch of each kernel family, per cloud (min-FLOP decomposition)
+def kernel_work(label: str, B: int):
+    """-> (flops, bytes) algorithmic per launch, or None"""
+    N, k = NPTS, KNN
+    if label.startswith("lpd_gemm["):
+        M, Nn, K, batch = (int(v) for v in label[9:-1].split("x"))
+        return 2.0 * M * Nn * K * batch, 4.0 * batch * (M * K + Nn * K + M * Nn)
+    if label.startswith("lpd_knn[C=64"):
+        return 2.0 * N * N * 64 * B, 4.0 * B * N * (64 + k)
+    if label.startswith("lpd_knn[C=3"):
+        return 2.0 * N * N * 3 * B, 4.0 * B * N * (3 + k)
+    if label.startswith("lpd_edgeconv_dg[128"):
+        return 2.0 * N * k * 128 * 128 * B, 4.0 * B * N * (256 + 256 + k)
+    if label.startswith("lpd_edge_gather_ext"):
+        C = int(label.split("C=")[1].rstrip("]"))
+        return 0.0, 4.0 * B * N * (2 * C + C + k)
+    if label == "lpd_netvlad_assign":
+        return 2.0 * N * 1024 * 64 * B, 4.0 * B * N * (1024 + 64)
+    return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc, self.index = None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if sm:
+            self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(device):
+    import torch
+    from lpdnet_b200 import synth
+    from lpdnet_b200.util.PointNetVlad import PointNetVlad
+    torch.manual_seed(1234)
+    model = PointNetVlad(num_points=NPTS, featnet="lpdnet", emb_dims=1024)   # random-init architecture, synthetic weights
+    sd = synth.synthetic_state_dict(model)
+    model.load_state_dict(sd)
+    return model.to(device).eval(), sd
+
+
+def cpu_baseline(n_clouds: int, threads: int, reps: int = 1):
+    """Times the CPU oracle (the reference's as-written forward: SGEMM + top-k kNN, materialised edge tensors,
+    un-folded BatchNorm) on `n_clouds` clouds of the workload, one cloud per host thread (numpy's element-wise ops
+    are single-threaded, so cloud-level parallelism is what uses all cores).  Returns (submaps/s, seconds)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from threadpoolctl import threadpool_limits
+    from lpdnet_b200 import synth
+    from lpdnet_b200.util.PointNetVlad import PointNetVlad
+    from oracle import model_numpy
+    shapes = {k: v.shape for k, v in PointNetVlad(num_points=NPTS, featnet="lpdnet", emb_dims=1024).state_dict().items()}
+    sd = {k: v.numpy() for k, v in synth.fill_state_dict(shapes).items()}
+    x = synth.clouds(n_clouds, NPTS).numpy()
+    model_numpy.KNN_IMPL = "blas"      # knn() as written (matmul + top-k); the canonical tie order is for parity only
+    best = float("inf")
+    try:
+        with threadpool_limits(limits=max(1, threads // max(1, min(threads, n_clouds)))):
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                with ThreadPoolExecutor(max_workers=min(threads, n_clouds)) as ex:
+                    outs = list(ex.map(lambda b: model_numpy.pointnetvlad_forward(sd, x[b:b + 1], featnet="lpdnet"), range(n_clouds)))
+                best = min(best, time.perf_counter() - t0)
+    finally:
+        model_numpy.KNN_IMPL = "canonical"
+    assert np.isfinite(np.concatenate(outs)).all()
+    return n_clouds / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = threads
+    _, t_full = cpu_baseline(sample, threads)            # warm-up (always one: page-in, BLAS thread pools)
+    if args.steps * t_full > 150.0:                       # keep the whole run within a few minutes
+        sample = max(1, int(threads * 150.0 / (args.steps * t_full)))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_baseline(sample, threads)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: LPD-Net eval embedding, 4096-pt submaps", "step": f"{sample} submaps per step on the host CPU, one per core (bounded sample of the 64-submap batch)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} submaps/step x {args.steps} steps, numpy+C oracle of the reference's as-written forward"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lpdnet_b200 import evaluate, ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU oracle")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    model, _ = build_model(device)
+    # per-rank shard of the synthetic submap stream: 4 distinct batches so consecutive steps never see the same input
+    n_rot = 4
+    host = [synth.clouds(BATCH, NPTS, seed=1234 + 97 * rank + i).pin_memory() for i in range(n_rot)]
+    dev_in = [h.to(device) for h in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def step(i):
+        with torch.no_grad():
+            return model(dev_in[i % n_rot])
+
+    for i in range(max(args.warmup, 3)):
+        out = step(i)
+    barrier()
+
+    # ---- device-resident throughput: K steps, each timed by its own event pair, L2 flushed (untimed) in between ----
+    ops.reset_launch_count()
+    evs = []
+    with ClockSampler(local) as clk:
+        barrier()
+        for i in range(args.steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = step(i)
+            e.record()
+            evs.append((s, e))
+        barrier()
+    launches = ops.launch_count()
+    t_ms = sum(s.elapsed_time(e) for s, e in evs)
+    t = torch.tensor([t_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t)
+    value = world * BATCH * args.steps / (t_ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host clouds -> descriptors in host memory ----
+    big = torch.cat([h[:, 0] for h in host], 0)                      # [4*64, N, 3] host
+    reps = max(1, (args.steps + n_rot - 1) // n_rot)
+    evaluate.get_latent_vectors(model, big[:BATCH].pin_memory(), batch_num=BATCH)   # warm
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    n_e2e = 0
+    for _ in range(reps):
+        desc = evaluate.get_latent_vectors(model, big, batch_num=BATCH)
+        n_e2e += big.shape[0]
+    e.record()
+    barrier()
+    te = torch.tensor([s.elapsed_time(e)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_e2e / (float(te) * 1e-3)
+
+    # ---- per-kernel device time of one step (separate, untimed-for-throughput pass) ----
+    roofline, breakdown = None, None
+    if rank == 0:
+        peaks = load_peaks()
+        per = {}
+        nprof = 3
+        for i in range(nprof):
+            flush.zero_()
+            ops.profile(True)
+            step(i)
+            rec = ops.profile(False)
+            torch.cuda.synchronize(device)
+            for label, a, b in rec:
+                per.setdefault(label, []).append(a.elapsed_time(b))
+        tot = {k_: sum(v) / nprof for k_, v in per.items()}                 # ms per step per kernel family
+        cnt = {k_: len(v) / nprof for k_, v in per.items()}
+        step_ms = sum(tot.values())
+        breakdown = {k_: {"ms_per_step": round(v, 4), "share": round(v / step_ms, 4), "launches": cnt[k_]}
+                     for k_, v in sorted(tot.items(), key=lambda kv: -kv[1])}
+        top = max(tot, key=tot.get)
+        work = kernel_work(top, BATCH)
+        if work is not None:
+            flops, byts = work
+            per_launch_ms = tot[top] / cnt[top]
+            tf = flops / (per_launch_ms * 1e-3) / 1e12
+            roofline = {"kernel": top, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained",
+                        "share_of_step": tot[top] / step_ms, "ms_per_launch": per_launch_ms,
+                        "note": "fp32 FFMA (CUDA-core) kernel graded against the dense bf16 tensor peak; algorithmic FLOPs per launch"}
+
+    if rank == 0:
+        threads = os.cpu_count() or 1
+        cpu_v, cpu_t = cpu_baseline(threads, threads)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C2: LPD-Net eval embedding (featnet=lpdnet, kNN k=20 graph features + NetVLAD K=64 D=1024 -> 256)",
+                           "submaps_per_gpu_per_step": BATCH, "points": NPTS, "sharding": f"batch-sharded dp{world}, no collective",
+                           "l2": "256 MiB memset between timed steps (untimed); 4 rotating input batches; intermediates > 1 GiB/step"},
+                "clocks": clk.result, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * NPTS * 3 * 4, "d2h_bytes_per_step": BATCH * 256 * 4,
+                        "api": "lpdnet_b200.evaluate.get_latent_vectors (pinned host clouds -> host descriptors)"},
+                "roofline": roofline, "kernel_breakdown": breakdown,
+                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": f"{threads} submaps (of the 64-submap batch) in {cpu_t:.1f} s, one per core, numpy oracle of the reference's as-written forward"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,41 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- launch accounting / per-call device timing (used by bench.py; off by default) ----------------------------
+_launches = 0          # kernels launched through this module since reset_launch_count()
+_profile = None        # None, or a list receiving (label, start_event, end_event)
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def profile(enable: bool):
+    """Start / stop recording one CUDA-event pair around every C-ABI call on the current stream."""
+    global _profile
+    rec, _profile = _profile, ([] if enable else None)
+    return rec
+
+
+def _call(label: str, nlaunch: int, fn, *args) -> None:
+    global _launches
+    if _profile is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _profile.append((label, s, e))
+    else:
+        rc = fn(*args)
+    _launches += nlaunch
+    _lib.check(rc, label)
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -34,10 +69,11 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
 def bn_fold(gamma, beta, mean, var, eps: float, bias=None):
     """(scale, shift) of an eval-mode BatchNorm, optionally absorbing a preceding conv bias."""
     lib = _lib.load()
+    _f32(mean, "running_mean")
     C = mean.numel()
     out = torch.empty(2, C, device=mean.device, dtype=torch.float32)
-    _lib.check(lib.lpd_bn_fold(_p(gamma), _p(beta), _p(mean), _p(var), _p(bias), float(eps), C,
-                               out[0].data_ptr(), out[1].data_ptr(), _stream()), "lpd_bn_fold")
+    _call("lpd_bn_fold", 1, lib.lpd_bn_fold, _p(gamma), _p(beta), _p(mean), _p(var), _p(bias), float(eps), C,
+                               out[0].data_ptr(), out[1].data_ptr(), _stream())
     return out[0], out[1]
 
 
@@ -47,7 +83,7 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
     x = _f32(x, "x").contiguous()
     b, R, Cc = x.shape
     out = torch.empty(b, Cc, R, device=x.device, dtype=torch.float32)
-    _lib.check(lib.lpd_transpose(x.data_ptr(), out.data_ptr(), b, R, Cc, _stream()), "lpd_transpose")
+    _call("lpd_transpose", 1, lib.lpd_transpose, x.data_ptr(), out.data_ptr(), b, R, Cc, _stream())
     return out
 
 
@@ -57,7 +93,7 @@ def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
     x_pm = _f32(x_pm, "x").contiguous()
     B, N, Cc = x_pm.shape
     idx = torch.empty(B, N, k, device=x_pm.device, dtype=torch.int64 if int64 else torch.int32)
-    _lib.check(lib.lpd_knn(x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64), _stream()), "lpd_knn")
+    _call(f"lpd_knn[C={Cc},k={k}]", 1, lib.lpd_knn, x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64), _stream())
     return idx
 
 
@@ -77,9 +113,9 @@ def gemm(A, B, *, a_layout=A_MK, b_layout=B_NK, M, N, K, lda=None, ldb=None, out
             strideC = M * N
     elif ldc is None:
         ldc = out.stride(-2)
-    _lib.check(lib.lpd_gemm(A.data_ptr(), a_layout, lda, strideA, B.data_ptr(), b_layout, ldb, strideB,
+    _call(f"lpd_gemm[{M}x{N}x{K}x{batch}]", 1, lib.lpd_gemm, A.data_ptr(), a_layout, lda, strideA, B.data_ptr(), b_layout, ldb, strideB,
                             out.data_ptr(), ldc, strideC, M, N, K, batch, _p(scale), _p(shift), act, float(slope),
-                            _p(aux), _stream()), "lpd_gemm")
+                            _p(aux), _stream())
     return out
 
 
@@ -87,22 +123,22 @@ def colmax(x: torch.Tensor, B: int, N: int, C: int, ldx: int | None = None) -> t
     lib = _lib.load()
     _f32(x, "x")
     out = torch.empty(B, C, device=x.device, dtype=torch.float32)
-    _lib.check(lib.lpd_colmax(x.data_ptr(), B, N, C, C if ldx is None else ldx, out.data_ptr(), _stream()), "lpd_colmax")
+    _call("lpd_colmax", 1, lib.lpd_colmax, x.data_ptr(), B, N, C, C if ldx is None else ldx, out.data_ptr(), _stream())
     return out
 
 
 def edge_gather_ext(p, ldp, q, ldq, idx, B, N, k, C, scale, shift, act, slope, out, ldo):
     lib = _lib.load()
-    _lib.check(lib.lpd_edge_gather_ext(p.data_ptr(), ldp, _p(q), ldq, idx.data_ptr(), B, N, k, C, _p(scale), _p(shift),
-                                       act, float(slope), out.data_ptr(), ldo, _stream()), "lpd_edge_gather_ext")
+    _call(f"lpd_edge_gather_ext[C={C}]", 1, lib.lpd_edge_gather_ext, p.data_ptr(), ldp, _p(q), ldq, idx.data_ptr(), B, N, k, C, _p(scale), _p(shift),
+                                       act, float(slope), out.data_ptr(), ldo, _stream())
     return out
 
 
 def edgeconv_dg(p, ldp, q, ldq, idx, B, N, k, C1, C2, s1, t1, w2, s2, t2, act, slope, x1, ld1, x2, ld2):
     lib = _lib.load()
-    _lib.check(lib.lpd_edgeconv_dg(p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), B, N, k, C1, C2,
+    _call(f"lpd_edgeconv_dg[{C1}x{C2}]", 1, lib.lpd_edgeconv_dg, p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), B, N, k, C1, C2,
                                    s1.data_ptr(), t1.data_ptr(), w2.data_ptr(), s2.data_ptr(), t2.data_ptr(),
-                                   act, float(slope), _p(x1), ld1, x2.data_ptr(), ld2, _stream()), "lpd_edgeconv_dg")
+                                   act, float(slope), _p(x1), ld1, x2.data_ptr(), ld2, _stream())
     return x1, x2
 
 
@@ -110,8 +146,8 @@ def netvlad_assign(x, M, D, wc, scale, shift, K=64, out=None):
     lib = _lib.load()
     if out is None:
         out = torch.empty(M, K, device=x.device, dtype=torch.float32)
-    _lib.check(lib.lpd_netvlad_assign(x.data_ptr(), M, D, wc.data_ptr(), _p(scale), _p(shift), K, out.data_ptr(),
-                                      _stream()), "lpd_netvlad_assign")
+    _call("lpd_netvlad_assign", 2, lib.lpd_netvlad_assign, x.data_ptr(), M, D, wc.data_ptr(), _p(scale), _p(shift), K, out.data_ptr(),
+                                      _stream())
     return out
 
 
@@ -119,16 +155,15 @@ def netvlad_finish(vlad, a, wc2, B, N, D, K=64):
     """in place on vlad [B, D, K]; returns it viewed as [B, D*K]."""
     lib = _lib.load()
     ws = torch.empty(B * 8 * K, device=vlad.device, dtype=torch.float32)
-    _lib.check(lib.lpd_netvlad_finish(vlad.data_ptr(), a.data_ptr(), wc2.data_ptr(), B, N, D, K, ws.data_ptr(),
-                                      _stream()), "lpd_netvlad_finish")
+    _call("lpd_netvlad_finish", 2, lib.lpd_netvlad_finish, vlad.data_ptr(), a.data_ptr(), wc2.data_ptr(), B, N, D, K, ws.data_ptr(),
+                                      _stream())
     return vlad.view(B, D * K)
 
 
 def splitk_reduce(part, splits, M, N, scale=None, shift=None):
     lib = _lib.load()
     out = torch.empty(M, N, device=part.device, dtype=torch.float32)
-    _lib.check(lib.lpd_splitk_reduce(part.data_ptr(), splits, M, N, _p(scale), _p(shift), out.data_ptr(), _stream()),
-               "lpd_splitk_reduce")
+    _call("lpd_splitk_reduce", 1, lib.lpd_splitk_reduce, part.data_ptr(), splits, M, N, _p(scale), _p(shift), out.data_ptr(), _stream())
     return out
 
 
@@ -145,9 +180,9 @@ def quadruplet_loss(q, pos, neg, other, m1, m2, use_min, lazy, ignore_zero_loss,
     if need_grad:
         grads = (torch.empty_like(q), torch.empty_like(pos), torch.empty_like(neg),
                  None if other is None else torch.empty_like(other))
-    _lib.check(lib.lpd_quadruplet_loss(q.data_ptr(), pos.data_ptr(), neg.data_ptr(), _p(other), Bq, P, Nn, D,
+    _call("lpd_quadruplet_loss", 1, lib.lpd_quadruplet_loss, q.data_ptr(), pos.data_ptr(), neg.data_ptr(), _p(other), Bq, P, Nn, D,
                                        float(m1), float(m2), flags, loss.data_ptr(), _p(grads[0]), _p(grads[1]),
-                                       _p(grads[2]), _p(grads[3]), _p(grad_out), _stream()), "lpd_quadruplet_loss")
+                                       _p(grads[2]), _p(grads[3]), _p(grad_out), _stream())
     return (loss, grads) if need_grad else loss
 
 
@@ -161,6 +196,6 @@ def retrieval_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_offset: int = 
     dist = torch.empty(Nq, k, device=db.device, dtype=torch.float64) if want_dist else None
     ws_bytes = lib.lpd_retrieval_workspace_bytes(Ndb, Nq, k)
     ws = torch.empty((ws_bytes + 7) // 8, device=db.device, dtype=torch.float64)
-    _lib.check(lib.lpd_retrieval_topk(db.data_ptr(), Ndb, q.data_ptr(), Nq, D, k, idx_offset, idx.data_ptr(), _p(dist),
-                                      ws.data_ptr(), ws.numel() * 8, _stream()), "lpd_retrieval_topk")
+    _call("lpd_retrieval_topk", 2, lib.lpd_retrieval_topk, db.data_ptr(), Ndb, q.data_ptr(), Nq, D, k, idx_offset, idx.data_ptr(), _p(dist),
+                                      ws.data_ptr(), ws.numel() * 8, _stream())
     return idx, dist

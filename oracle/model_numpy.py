@@ -64,8 +64,25 @@ def relu(x):
     return np.maximum(x, 0).astype(f32)
 
 
+KNN_IMPL = "canonical"   # "canonical": bit-exact tie-by-index target (parity) | "blas": as written (timing baseline)
+
+
+def knn_blas(x, k):
+    """knn() exactly as written in the reference (:317-326): SGEMM inner product, two subtractions, top-k —
+    BLAS accumulation order and unspecified tie order, like torch.  Used for the CPU timing baseline only."""
+    inner = -2 * np.matmul(x.transpose(0, 2, 1), x)
+    xx = np.sum(x ** 2, axis=1, keepdims=True)
+    pd = -xx - inner
+    pd = pd - xx.transpose(0, 2, 1)
+    part = np.argpartition(-pd, k - 1, axis=-1)[..., :k]
+    order = np.argsort(-np.take_along_axis(pd, part, -1), axis=-1, kind="stable")
+    return np.take_along_axis(part, order, -1)
+
+
 def knn(x, k):
-    """x [B, C, N] -> idx [B, N, k] (canonical tie order)."""
+    """x [B, C, N] -> idx [B, N, k] (canonical tie order unless KNN_IMPL == "blas")."""
+    if KNN_IMPL == "blas":
+        return knn_blas(x, k)
     return knn_canonical(np.ascontiguousarray(x.transpose(0, 2, 1)), k)
 
 

@@ -1,0 +1,231 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle / a float64 numpy restatement,
+on seeded inputs, including ragged and edge shapes.  Runs on the B200 box (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from lpdnet_b200 import ops, synth
+from oracle import knn_canonical, loss_numpy, retrieval_bruteforce
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ------------------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("B,N,C,k", [
+    (2, 1024, 3, 20), (2, 512, 64, 20), (1, 1000, 3, 20), (3, 130, 64, 20), (1, 257, 3, 32),
+    (1, 64, 8, 1), (1, 33, 16, 32), (2, 200, 5, 7), (1, 4096, 3, 20), (1, 2048, 64, 32),
+])
+def test_knn_bit_exact_vs_canonical_oracle(cuda, B, N, C, k):
+    r = rng(B * 1000 + N + C)
+    x = (r.uniform(-1, 1, (B, N, C)) if C <= 8 else np.maximum(r.standard_normal((B, N, C)), 0.01 * r.standard_normal((B, N, C)))).astype(np.float32)
+    want = knn_canonical(x, k)
+    got = ops.knn(dev(x), k).cpu().numpy()
+    assert got.dtype == np.int32
+    assert np.array_equal(got, want)
+    got64 = ops.knn(dev(x), k, int64=True).cpu().numpy()
+    assert got64.dtype == np.int64 and np.array_equal(got64, want)
+
+
+def test_knn_exact_ties_and_duplicates(cuda):
+    lat = np.stack(np.meshgrid(np.arange(8.), np.arange(8.), np.arange(8.), indexing="ij"), 0).reshape(3, 512).T
+    x = synth.clouds(1, 1024)[0, 0].numpy().copy()
+    x[500:510] = x[0:10]  # exact duplicate points
+    for cloud in (lat.astype(np.float32), x):
+        want = knn_canonical(cloud[None], 20)
+        got = ops.knn(dev(cloud[None]), 20).cpu().numpy()
+        assert np.array_equal(got, want)
+
+
+def test_knn_matches_reference_golden_sets(cuda, golden):
+    """against the reference's own torch knn() output (tie-aware: sets may differ only on near-ties)"""
+    from _helpers import assert_knn_equivalent
+    g = golden("knn")
+    x = synth.clouds(2, 1024)[:, 0].contiguous()
+    got = ops.knn(x.cuda(), 20).cpu().numpy()
+    assert assert_knn_equivalent(x.numpy(), got, g["xyz_idx"].astype(np.int64), 20) <= 8
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(130, 70, 19), (64, 64, 64), (257, 128, 3), (1000, 1024, 512), (5, 256, 1024), (300, 64, 1024)])
+@pytest.mark.parametrize("al", [ops.A_MK, ops.A_KM])
+@pytest.mark.parametrize("bl", [ops.B_NK, ops.B_KN])
+def test_gemm_layouts_and_ragged_shapes(cuda, M, N, K, al, bl):
+    r = rng(M + 7 * N + 13 * K)
+    A = r.standard_normal((M, K)).astype(np.float32)
+    Bm = r.standard_normal((K, N)).astype(np.float32)
+    scale = r.standard_normal(N).astype(np.float32)
+    shift = r.standard_normal(N).astype(np.float32)
+    ref = (A.astype(np.float64) @ Bm.astype(np.float64)) * scale + shift
+    ref = np.where(ref > 0, ref, 0.01 * ref)
+    a_dev = dev(A if al == ops.A_MK else A.T)
+    b_dev = dev(Bm.T if bl == ops.B_NK else Bm)
+    out = ops.gemm(a_dev, b_dev, a_layout=al, b_layout=bl, M=M, N=N, K=K, scale=dev(scale), shift=dev(shift),
+                   act=ops.ACT_LEAKY, slope=0.01).cpu().numpy()
+    assert np.abs(out - ref).max() < max(2e-6 * np.abs(ref).max(), 1e-5)
+
+
+def test_gemm_batched_strided_gate_and_ldc(cuda):
+    r = rng(5)
+    b, M, N, K = 3, 70, 96, 40
+    A = r.standard_normal((b, M, K)).astype(np.float32)
+    Bm = r.standard_normal((b, N, K)).astype(np.float32)
+    aux = r.standard_normal((b, M, N)).astype(np.float32)
+    ref = np.einsum("bmk,bnk->bmn", A.astype(np.float64), Bm.astype(np.float64))
+    ref = aux / (1 + np.exp(-ref))
+    out = ops.gemm(dev(A), dev(Bm), M=M, N=N, K=K, batch=b, strideA=M * K, strideB=N * K, act=ops.ACT_GATE, aux=dev(aux))
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-4
+    # write into a column window of a wider buffer (the concat-free layout of the feature pyramid)
+    wide = torch.zeros(M, 256, device="cuda")
+    ops.gemm(dev(A[0]), dev(Bm[0]), M=M, N=N, K=K, out=wide[:, 128:], ldc=256)
+    ref0 = A[0].astype(np.float64) @ Bm[0].astype(np.float64).T
+    assert np.abs(wide[:, 128:128 + N].cpu().numpy() - ref0).max() < 1e-4
+    assert float(wide[:, :128].abs().max()) == 0.0 and float(wide[:, 128 + N:].abs().max()) == 0.0
+
+
+def test_bn_fold_transpose_colmax_splitk(cuda):
+    r = rng(11)
+    C = 130
+    g, b, m = (r.standard_normal(C).astype(np.float32) for _ in range(3))
+    v = r.uniform(0.5, 2, C).astype(np.float32)
+    bias = r.standard_normal(C).astype(np.float32)
+    s, t = ops.bn_fold(dev(g), dev(b), dev(m), dev(v), 1e-5, bias=dev(bias))
+    s_ref = g / np.sqrt(v.astype(np.float64) + 1e-5)
+    assert np.abs(s.cpu().numpy() - s_ref).max() < 1e-6
+    assert np.abs(t.cpu().numpy() - (b - m * s_ref + bias * s_ref)).max() < 1e-5
+    x = r.standard_normal((3, 77, 45)).astype(np.float32)
+    assert np.array_equal(ops.transpose(dev(x)).cpu().numpy(), x.transpose(0, 2, 1))
+    assert np.array_equal(ops.colmax(dev(x), 3, 77, 45).cpu().numpy(), x.max(1))
+    part = r.standard_normal((9, 6, 20)).astype(np.float32)
+    out = ops.splitk_reduce(dev(part), 9, 6, 20, scale=dev(g[:20]), shift=dev(b[:20])).cpu().numpy()
+    assert np.abs(out - (part.astype(np.float64).sum(0) * g[:20] + b[:20])).max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ EdgeConv
+def _leaky(x):
+    return np.where(x > 0, x, 0.01 * x)
+
+
+@pytest.mark.parametrize("B,N,k,C", [(2, 300, 20, 256), (1, 257, 7, 128), (2, 128, 32, 64)])
+def test_edge_gather_ext_vs_materialised_edges(cuda, B, N, k, C):
+    r = rng(N + C)
+    p = r.standard_normal((B * N, C)).astype(np.float32)
+    q = r.standard_normal((B * N, C)).astype(np.float32)
+    idx = r.integers(0, N, (B, N, k)).astype(np.int32)
+    s = r.standard_normal(C).astype(np.float32)  # negative scales included (min branch)
+    t = r.standard_normal(C).astype(np.float32)
+    pb = p.reshape(B, N, C)
+    edges = pb[np.arange(B)[:, None, None], idx] + q.reshape(B, N, 1, C)      # [B,N,k,C]
+    ref = _leaky(edges.astype(np.float64) * s + t).max(2).reshape(B * N, C)
+    out = torch.empty(B * N, C, device="cuda")
+    ops.edge_gather_ext(dev(p), C, dev(q), C, dev(idx, torch.int32), B, N, k, C, dev(s), dev(t), ops.ACT_LEAKY, 0.01, out, C)
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-5
+    # gather-only edges (LPDNetOrign, cat=False)
+    ref2 = pb[np.arange(B)[:, None, None], idx].max(2).reshape(B * N, C)
+    ops.edge_gather_ext(dev(p), C, None, 0, dev(idx, torch.int32), B, N, k, C, None, None, ops.ACT_NONE, 0.0, out, C)
+    assert np.array_equal(out.cpu().numpy(), ref2)
+
+
+@pytest.mark.parametrize("B,N,k,C", [(2, 300, 20, 128), (1, 257, 32, 128), (1, 100, 7, 128), (2, 200, 20, 64), (1, 90, 25, 64)])
+def test_edgeconv_dg_vs_materialised_edges(cuda, B, N, k, C):
+    r = rng(N + k + C)
+    pq = r.standard_normal((B * N, 2 * C)).astype(np.float32)
+    idx = r.integers(0, N, (B, N, k)).astype(np.int32)
+    s1, t1, s2, t2 = (r.standard_normal(C).astype(np.float32) for _ in range(4))
+    w2 = (r.standard_normal((C, C)) / np.sqrt(C)).astype(np.float32)
+    P, Q = pq[:, :C].reshape(B, N, C), pq[:, C:].reshape(B, N, C)
+    y1 = _leaky((P[np.arange(B)[:, None, None], idx] + Q[:, :, None, :]).astype(np.float64) * s1 + t1)   # [B,N,k,C]
+    y2 = _leaky((y1 @ w2.astype(np.float64).T) * s2 + t2)
+    x1_ref, x2_ref = y1.max(2).reshape(B * N, C), y2.max(2).reshape(B * N, C)
+    d_pq = dev(pq)
+    x = torch.zeros(B * N, 2 * C, device="cuda")
+    ops.edgeconv_dg(d_pq, 2 * C, d_pq[:, C:], 2 * C, dev(idx, torch.int32), B, N, k, C, C, dev(s1), dev(t1), dev(w2), dev(s2), dev(t2),
+                    ops.ACT_LEAKY, 0.01, x, 2 * C, x[:, C:], 2 * C)
+    got = x.cpu().numpy()
+    assert np.abs(got[:, :C] - x1_ref).max() < 1e-5
+    assert np.abs(got[:, C:] - x2_ref).max() < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ NetVLAD
+def test_netvlad_assign_and_finish(cuda):
+    r = rng(3)
+    B, N, D, K = 2, 300, 256, 64
+    x = r.standard_normal((B * N, D)).astype(np.float32)
+    wc = (r.standard_normal((D, K)) / np.sqrt(D)).astype(np.float32)
+    wc2 = (r.standard_normal((D, K)) / np.sqrt(D)).astype(np.float32)
+    s, t = r.standard_normal(K).astype(np.float32), r.standard_normal(K).astype(np.float32)
+    z = (x.astype(np.float64) @ wc) * s + t
+    a_ref = np.exp(z - z.max(1, keepdims=True))
+    a_ref /= a_ref.sum(1, keepdims=True)
+    a = ops.netvlad_assign(dev(x), B * N, D, dev(wc), dev(s), dev(t))
+    assert np.abs(a.cpu().numpy() - a_ref).max() < 1e-5
+    # aggregate with lpd_gemm (A = x^T stored [K=N][M=D], B = a stored [K=N][N=K]) then finish
+    vraw = ops.gemm(dev(x), a, a_layout=ops.A_KM, b_layout=ops.B_KN, M=D, N=K, K=N, lda=D, ldb=K, batch=B,
+                    strideA=N * D, strideB=N * K)
+    a3, x3 = a_ref.reshape(B, N, K), x.reshape(B, N, D).astype(np.float64)
+    v = np.einsum("bnd,bnk->bdk", x3, a3) - a3.sum(1)[:, None, :] * wc2[None]
+    assert np.abs(vraw.cpu().numpy() - np.einsum("bnd,bnk->bdk", x3, a3)).max() < 1e-4
+    v = v / np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-12)
+    v = v.reshape(B, D * K)
+    v = v / np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-12)
+    out = ops.netvlad_finish(vraw, a, dev(wc2), B, N, D, K)
+    assert np.abs(out.cpu().numpy() - v).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ loss
+def test_loss_forward_backward_vs_reference_golden(cuda, golden):
+    g = golden("loss")
+    for tag in ("2_2_18", "3_1_2", "5_4_7"):
+        q, pos, neg, other = (dev(g[f"{tag}.{n}"]) for n in ("q", "pos", "neg", "other"))
+        for um in (0, 1):
+            for lz in (0, 1):
+                for ig in (0, 1):
+                    ft = f"{tag}.{um}{lz}{ig}"
+                    loss, grads = ops.quadruplet_loss(q, pos, neg, other, 0.5, 0.2, um, lz, ig, need_grad=True)
+                    ref = float(g[ft + ".quad"])
+                    assert abs(float(loss) - ref) <= 1e-5 * abs(ref), ft  # north_star: 1e-5 relative
+                    for a, n in zip(grads, ("gq", "gpos", "gneg", "gother")):
+                        r_ = g[f"{ft}.quad.{n}"]
+                        assert np.abs(a.cpu().numpy() - r_).max() <= 1e-5 * max(1.0, np.abs(r_).max()), (ft, n)
+                    loss, grads = ops.quadruplet_loss(q, pos, neg, None, 0.5, 0.2, um, lz, ig, need_grad=True)
+                    ref = float(g[ft + ".trip"])
+                    assert abs(float(loss) - ref) <= 1e-5 * abs(ref), ft
+                    for a, n in zip(grads[:3], ("gq", "gpos", "gneg")):
+                        r_ = g[f"{ft}.trip.{n}"]
+                        assert np.abs(a.cpu().numpy() - r_).max() <= 1e-5 * max(1.0, np.abs(r_).max()), (ft, n)
+    # zero-loss tuples + ignore_zero_loss, checked against the numpy oracle
+    r = rng(4)
+    q = r.standard_normal((4, 1, 32)).astype(np.float32) * 0.1
+    pos = q + 0.01 * r.standard_normal((4, 2, 32)).astype(np.float32)
+    neg = q + 0.05 * r.standard_normal((4, 6, 32)).astype(np.float32)
+    neg[1] += 5.0  # tuple 1 has zero loss
+    other = q + 0.05 * r.standard_normal((4, 1, 32)).astype(np.float32)
+    for lz in (0, 1):
+        ref = loss_numpy.quadruplet_loss(q, pos, neg, other, 0.5, 0.2, True, bool(lz), True)
+        got = ops.quadruplet_loss(dev(q), dev(pos), dev(neg), dev(other), 0.5, 0.2, 1, lz, 1)
+        assert abs(float(got) - ref) <= 1e-5 * abs(ref)
+
+
+# ------------------------------------------------------------------------------------------------ retrieval
+@pytest.mark.parametrize("Ndb,Nq,D,k", [(956, 132, 256, 25), (21988, 300, 256, 25), (70, 5, 256, 25), (20, 3, 64, 25), (1000, 65, 30, 10)])
+def test_retrieval_topk_vs_bruteforce_oracle(cuda, Ndb, Nq, D, k):
+    r = rng(Ndb + Nq)
+    db = r.standard_normal((Ndb, D)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    q = (db[r.integers(0, Ndb, Nq)] + 0.3 * r.standard_normal((Nq, D)) / np.sqrt(D)).astype(np.float32)
+    if Ndb > 100:
+        db[50] = db[7]  # exact duplicate rows: tie broken towards the lower index
+    want_idx, want_d = retrieval_bruteforce(db, q, k)
+    idx, dist = ops.retrieval_topk(dev(db), dev(q), k)
+    assert np.array_equal(idx.cpu().numpy(), want_idx)
+    fin = np.isfinite(want_d)
+    assert np.array_equal(dist.cpu().numpy()[fin], want_d[fin])
+    idx2, _ = ops.retrieval_topk(dev(db), dev(q), k, idx_offset=1000, want_dist=False)
+    assert np.array_equal(idx2.cpu().numpy()[want_idx >= 0], want_idx[want_idx >= 0] + 1000)
