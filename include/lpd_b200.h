@@ -105,6 +105,18 @@ int lpd_gemm(const float* A, int a_layout, int lda, long long strideA,
              const float* scale, const float* shift, int act, float slope, const float* aux,
              void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core GEMM ("fast" arithmetic): same contract as lpd_gemm for the conv / linear case
+ *     C[m][n] = act( scale[n] * sum_k A[m][k] * B[n][k] + shift[n] ),   A [M][K], B [N][K] K-contiguous,
+ * executed with TMA-fed tcgen05.mma kind::tf32 (operands rounded to TF32 by the tensor core, fp32
+ * accumulation in TMEM).  Requires sm_100, lda/ldb/ldc multiples of 4 and 16-byte aligned bases.
+ * N % 4 == 0; act in {NONE, RELU, LEAKY with 0 <= slope <= 1}.  Replaces the same call sites as lpd_gemm where the stated
+ * TF32 tolerance applies ("precision modes").
+ * ------------------------------------------------------------------------------------------- */
+int lpd_gemm_tf32(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                  int M, int N, int K, const float* scale, const float* shift, int act, float slope,
+                  void* stream);
+
 /* column max over rows of each cloud: out[b][c] = max_n x[b][n][c]
  * (MaxPool2d((num_points,1)) PointNetVlad.py:137,169 ; torch.max(x,2) lpdnet_model.py:300) */
 int lpd_colmax(const float* x, int B, int N, int C, int ldx, float* out, void* stream);

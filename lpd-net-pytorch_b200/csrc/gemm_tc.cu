@@ -1,0 +1,321 @@
+// Tensor-core GEMM for sm_100a: TMA-fed, tcgen05.mma kind::tf32, fp32 accumulators in TMEM, fused
+// per-column affine + activation epilogue.  "fast" arithmetic path for the dense 1x1-conv / matmul layers
+// (reference lpdnet_model.py:249-262 conv stacks, PointNetVlad.py:48 soft-assignment) — fp32 operands are
+// consumed as TF32 (10-bit mantissa) by the tensor core, products accumulate in fp32.
+//
+//     C[m][n] = act(scale[n] * sum_k A[m][k] * B[n][k] + shift[n])      A [M][K], B [N][K], both K-contiguous
+//
+// Persistent warp-specialised CTA (one per SM), 320 threads:
+//   warp 0    TMA producer: cp.async.bulk.tensor 2-D boxes (128B swizzle) of A (128 x 32 fp32) and B (BN x 32 fp32)
+//             into a STAGES-deep shared-memory ring, completion on mbarriers
+//   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=8) x4 per ring slot, tcgen05.commit
+//             releases the slot; two accumulator stages in TMEM so the epilogue of tile i overlaps tile i+1
+//   warps 2-9 epilogue (two per TMEM lane quarter, each owning half of the tile's columns): tcgen05.ld 32 lanes x
+//             32 columns, raw accumulators transposed through an XOR-swizzled 4 KB per-warp staging buffer, then
+//             affine + activation applied on the way out so that every st.global.v4 instruction writes four full
+//             128-byte lines.  (TMA stores were measured slower here: they queue behind the producer's prefetch.)
+#include "common.cuh"
+#include <cuda.h>
+
+namespace lpd {
+namespace tc {
+
+constexpr int BM = 128;      // UMMA M
+constexpr int BK = 32;       // fp32 elements per smem row = 128 bytes = one swizzle span
+constexpr int UMMA_K = 8;    // tf32
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address  [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows x 128 B [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell) [46,48)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B [61,64)
+    return d;
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Params {
+    float* C; int ldc; int M, N, K;
+    const float* scale; const float* shift;
+    float neg_slope;   // act(v) = max(v, v * neg_slope): 1 -> identity, 0 -> ReLU, 0 < s < 1 -> LeakyReLU(s)
+    int tiles_m, tiles_n;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
+    constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two >= 32 for BN in {64,128,256})
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();       // 128B-swizzle atoms need 1024-byte aligned tiles
+    float* cstage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [EPI_WARPS][32 rows][32 cols]
+    uint64_t* full = reinterpret_cast<uint64_t*>(cstage + EPI_WARPS * 32 * 32);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m0);
+                    tma_load_2d(sa + A_BYTES, &tmap_b, &full[stage], kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        tc_mma_tf32(tmem_d, da + (uint64_t)(k * UMMA_K * 4 >> 4), db + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&empty[stage]);           // slot reusable once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[acc]);                 // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                // which half of the tile's column chunks this warp owns
+        constexpr int CPW = BN / 64;                     // 32-column chunks per warp
+        float* stg = cstage + (warp - 2) * (32 * 32);
+        const int ch = lane & 7, rsub = lane >> 3;       // read-back role: 16-byte chunk within the row, row sub-index
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int row0 = m0 + q * 32;
+#pragma unroll 1
+            for (int i = 0; i < CPW; ++i) {
+                const int c = half * CPW + i;
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N || row0 >= p.M) break;  // warp-uniform: the rest is out of range
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+                float* dst = stg + lane * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)              // lane = row: raw accumulators, 16B chunk ^= row & 7
+                    *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                const int col = col0 + ch * 4;           // this lane's 4 columns for the whole chunk
+                const bool col_ok = col < p.N;           // N % 4 == 0
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col_ok) {
+                    if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+                    if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+                }
+                float* gcol = p.C + (size_t)row0 * p.ldc + col;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rsub;
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((ch ^ (rr & 7)) << 2));
+                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    v.x = fmaxf(v.x, v.x * p.neg_slope); v.y = fmaxf(v.y, v.y * p.neg_slope);
+                    v.z = fmaxf(v.z, v.z * p.neg_slope); v.w = fmaxf(v.w, v.w * p.neg_slope);
+                    if (col_ok && row0 + rr < p.M) *reinterpret_cast<float4*>(gcol + (size_t)rr * p.ldc) = v;
+                }
+                __syncwarp();                            // staging buffer is rewritten by the next chunk
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [rows][cols] with leading dimension ld (elements), box = [box_rows][32 cols], 128B swizzle
+static int make_tmap(CUtensorMap* m, const float* base, long long rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled entry point not found"); return LPD_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return LPD_ECUDA; }
+    return LPD_OK;
+}
+
+template <int BN, int STAGES>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + EPI_WARPS * 32 * 32 * 4 + 256;
+    LPD_CUDA_CHECK(allow_smem(gemm_tf32_kernel<BN, STAGES>, smem));
+    int dev = 0, sms = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    p.tiles_m = ceil_div(p.M, BM);
+    p.tiles_n = ceil_div(p.N, BN);
+    const long long tiles = (long long)p.tiles_m * p.tiles_n;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gemm_tf32_kernel<BN, STAGES><<<grid, THREADS, smem, st>>>(ta, tb, p);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+}  // namespace tc
+}  // namespace lpd
+
+extern "C" int lpd_gemm_tf32(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                             int M, int N, int K, const float* scale, const float* shift, int act, float slope,
+                             void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1);
+    LPD_REQUIRE(lda >= K && ldb >= K && ldc >= N);
+    LPD_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0);          // 16-byte global strides (TMA) / float4 stores
+    LPD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0);
+    LPD_REQUIRE((N % 4) == 0);
+    LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || (act == LPD_ACT_LEAKY && slope >= 0.f && slope <= 1.f));
+    int dev = 0, major = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return LPD_EUNSUPPORTED;
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    CUtensorMap ta, tb;
+    int rc = tc::make_tmap(&ta, A, M, K, lda, tc::BM);
+    if (rc != LPD_OK) return rc;
+    rc = tc::make_tmap(&tb, B, N, K, ldb, BN);
+    if (rc != LPD_OK) return rc;
+    tc::Params p;
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = scale; p.shift = shift;
+    p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
+    p.tiles_m = p.tiles_n = 0;
+    cudaStream_t st = as_stream(stream);
+    if (BN == 64) return tc::launch<64, 8>(ta, tb, p, st);
+    if (BN == 128) return tc::launch<128, 6>(ta, tb, p, st);
+    return tc::launch<256, 4>(ta, tb, p, st);
+}

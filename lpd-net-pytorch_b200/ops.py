@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import (ACT_GATE, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, A_KM, A_MK, B_KN, B_NK)
 
 __all__ = ["bn_fold", "transpose", "knn", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
-           "netvlad_assign", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
+           "gemm_tf32", "linear", "set_precision", "get_precision", "netvlad_assign", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
            "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ACT_SIGMOID", "ACT_GATE", "A_MK", "A_KM", "B_NK", "B_KN"]
 
 
@@ -117,6 +117,49 @@ def gemm(A, B, *, a_layout=A_MK, b_layout=B_NK, M, N, K, lda=None, ldb=None, out
                             out.data_ptr(), ldc, strideC, M, N, K, batch, _p(scale), _p(shift), act, float(slope),
                             _p(aux), _stream())
     return out
+
+
+# ---- precision mode of the dense conv / linear layers ----------------------------------------------------------
+#   "fp32": every GEMM on the CUDA cores (lpd_gemm, plain FFMA)        — strict parity mode
+#   "tf32": large K-contiguous GEMMs on the tensor cores (lpd_gemm_tf32) — fast mode, TF32 operand rounding
+_precision = "fp32"
+
+
+def set_precision(mode: str) -> str:
+    """Select "fp32" (strict) or "tf32" (tensor cores); returns the previous mode."""
+    global _precision
+    if mode not in ("fp32", "tf32"):
+        raise ValueError("precision must be 'fp32' or 'tf32'")
+    prev, _precision = _precision, mode
+    return prev
+
+
+def get_precision() -> str:
+    return _precision
+
+
+def gemm_tf32(A, W, *, M, N, K, lda=None, out=None, ldc=None, scale=None, shift=None, act=ACT_NONE, slope=0.0):
+    """out[m][n] = act(scale[n] * sum_k A[m][k] W[n][k] + shift[n]) on the tensor cores (TF32)."""
+    lib = _lib.load()
+    _f32(A, "A"), _f32(W, "W")
+    lda = K if lda is None else lda
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+        ldc = N
+    elif ldc is None:
+        ldc = out.stride(-2)
+    _call(f"lpd_gemm_tf32[{M}x{N}x{K}]", 1, lib.lpd_gemm_tf32, A.data_ptr(), lda, W.data_ptr(), K, out.data_ptr(), ldc,
+          M, N, K, _p(scale), _p(shift), act, float(slope), _stream())
+    return out
+
+
+def linear(A, W, *, M, N, K, lda=None, out=None, ldc=None, scale=None, shift=None, act=ACT_NONE, slope=0.0):
+    """conv1x1 / linear layer y = act(scale * (A . W^T) + shift) with W [N, K]; dispatches on the precision mode."""
+    lda_ = K if lda is None else lda
+    if (_precision == "tf32" and K >= 32 and K % 4 == 0 and lda_ % 4 == 0 and N >= 64 and N % 4 == 0 and M >= 128
+            and (ldc is None or ldc % 4 == 0) and A.data_ptr() % 16 == 0 and (out is None or out.data_ptr() % 16 == 0)):
+        return gemm_tf32(A, W, M=M, N=N, K=K, lda=lda, out=out, ldc=ldc, scale=scale, shift=shift, act=act, slope=slope)
+    return gemm(A, W, M=M, N=N, K=K, lda=lda, out=out, ldc=ldc, scale=scale, shift=shift, act=act, slope=slope)
 
 
 def colmax(x: torch.Tensor, B: int, N: int, C: int, ldx: int | None = None) -> torch.Tensor:

@@ -229,3 +229,26 @@ def test_retrieval_topk_vs_bruteforce_oracle(cuda, Ndb, Nq, D, k):
     assert np.array_equal(dist.cpu().numpy()[fin], want_d[fin])
     idx2, _ = ops.retrieval_topk(dev(db), dev(q), k, idx_offset=1000, want_dist=False)
     assert np.array_equal(idx2.cpu().numpy()[want_idx >= 0], want_idx[want_idx >= 0] + 1000)
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core GEMM
+@pytest.mark.parametrize("M,N,K,ldx", [(1000, 1024, 512, 0), (128, 64, 1024, 0), (300, 512, 128, 0), (4096, 256, 64, 0),
+                                       (777, 200, 96, 0), (2048, 128, 128, 512), (130, 1024, 40, 0)])
+def test_gemm_tf32_tensor_core_path(cuda, M, N, K, ldx):
+    """tcgen05 kind::tf32: operands are rounded to TF32 (10-bit mantissa) -> tolerance 2^-9 of the result scale."""
+    r = rng(M + N + K)
+    lda = ldx if ldx else K
+    A = r.standard_normal((M, lda)).astype(np.float32)
+    W = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    scale, shift = r.standard_normal(N).astype(np.float32), r.standard_normal(N).astype(np.float32)
+    ref = (A[:, :K].astype(np.float64) @ W.astype(np.float64).T) * scale + shift
+    ref = np.where(ref > 0, ref, 0.01 * ref)
+    wide = torch.zeros(M, N + 64, device="cuda")
+    ops.gemm_tf32(dev(A), dev(W), M=M, N=N, K=K, lda=lda, out=wide[:, 32:], ldc=N + 64, scale=dev(scale), shift=dev(shift),
+                  act=ops.ACT_LEAKY, slope=0.01)
+    got = wide.cpu().numpy()
+    assert np.abs(got[:, 32:32 + N] - ref).max() < 2.0 ** -9 * np.abs(ref).max()
+    assert not got[:, :32].any() and not got[:, 32 + N:].any()        # nothing written outside the column window
+    # and it agrees with the strict fp32 path to TF32 accuracy
+    strict = ops.gemm(dev(A), dev(W), M=M, N=N, K=K, lda=lda, scale=dev(scale), shift=dev(shift), act=ops.ACT_LEAKY, slope=0.01)
+    assert np.abs(strict.cpu().numpy() - got[:, 32:32 + N]).max() < 2.0 ** -9 * np.abs(ref).max()
