@@ -156,6 +156,10 @@ int lpd_edgeconv_dg(const float* p, int ldp, const float* q, int ldq,
 int lpd_netvlad_assign(const float* x, int M, int D, const float* wc, const float* scale,
                        const float* shift, int K, float* a, void* stream);
 
+/* in-place row softmax over exactly 64 columns: a[m][:] = softmax(a[m][:])  (PointNetVlad.py:58, the
+ * second half of lpd_netvlad_assign, exposed for the tensor-core assignment path) */
+int lpd_softmax64(float* a, long long M, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * NetVLAD residual + normalisations, in place on the raw aggregate
  *     vraw[b][d][k] = sum_n a[b][n][k] * x[b][n][d]     (computed with lpd_gemm, A_KM x B_KN)

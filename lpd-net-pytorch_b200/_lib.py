@@ -38,6 +38,7 @@ SIGNATURES = {
     "lpd_edgeconv_dg": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f,
                              _vp, _i, _vp, _i, _vp]),
     "lpd_netvlad_assign": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    "lpd_softmax64": (_i, [_vp, _ll, _vp]),
     "lpd_netvlad_finish": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "lpd_splitk_reduce": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lpd_quadruplet_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -184,6 +184,106 @@ static int knn_launch(const float* x, int B, int N, int C, int k, void* idx, int
     return LPD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// xyz kNN (C <= 3): no distance GEMM worth tiling, so the kernel is organised around the selection.
+// The cloud is packed once per CTA into shared memory as float4 (x, y, z, xx).  Every warp owns 4 query
+// rows; each lane evaluates one candidate per step against the 4 rows (6 FP32 ops per pair, canonical
+// order), one compare + ballot per row filters against the row's current k-th value, and the rare
+// survivors are inserted into the warp-resident sorted list with shuffles.  No block-level barrier
+// inside the scan.
+// ------------------------------------------------------------------------------------------------
+constexpr int KNN3_WARPS = 8;
+constexpr int KNN3_RPW = 4;                       // query rows per warp
+constexpr int KNN3_ROWS = KNN3_WARPS * KNN3_RPW;  // 32 query rows per CTA
+constexpr int KNN3_CHUNK = 4096;                  // candidates resident in shared memory at a time (64 KB)
+
+__global__ void __launch_bounds__(KNN3_WARPS * 32)
+knn3_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ idx_out, int idx_i64) {
+    extern __shared__ __align__(16) float4 cand[];   // [min(N, KNN3_CHUNK)]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const float* xb = x + (size_t)b * N * C;
+    const int row0 = blockIdx.x * KNN3_ROWS + warp * KNN3_RPW;
+
+    float qx[KNN3_RPW], qy[KNN3_RPW], qz[KNN3_RPW], qq[KNN3_RPW];
+    float lv[KNN3_RPW], tv[KNN3_RPW];
+    int li[KNN3_RPW];
+#pragma unroll
+    for (int r = 0; r < KNN3_RPW; ++r) {
+        const int row = min(row0 + r, N - 1);
+        const float* p = xb + (size_t)row * C;
+        qx[r] = __ldg(p);
+        qy[r] = C > 1 ? __ldg(p + 1) : 0.f;
+        qz[r] = C > 2 ? __ldg(p + 2) : 0.f;
+        qq[r] = __fmaf_rn(qz[r], qz[r], __fmaf_rn(qy[r], qy[r], __fmaf_rn(qx[r], qx[r], 0.f)));
+        lv[r] = -INFINITY; li[r] = INT_MAX; tv[r] = -INFINITY;
+    }
+
+    for (int c0 = 0; c0 < N; c0 += KNN3_CHUNK) {
+        const int cn = min(KNN3_CHUNK, N - c0);
+        __syncthreads();                              // previous chunk fully scanned
+        for (int i = tid; i < cn; i += KNN3_WARPS * 32) {
+            const float* p = xb + (size_t)(c0 + i) * C;
+            float4 v;
+            v.x = __ldg(p);
+            v.y = C > 1 ? __ldg(p + 1) : 0.f;
+            v.z = C > 2 ? __ldg(p + 2) : 0.f;
+            v.w = __fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, __fmaf_rn(v.x, v.x, 0.f)));
+            cand[i] = v;
+        }
+        __syncthreads();
+        for (int j0 = 0; j0 < cn; j0 += 32) {
+            const int jl = j0 + lane;
+            const bool valid = jl < cn;
+            const float4 cv = cand[valid ? jl : 0];
+            const int j = c0 + jl;
+#pragma unroll
+            for (int r = 0; r < KNN3_RPW; ++r) {
+                const float dot = __fmaf_rn(qz[r], cv.z, __fmaf_rn(qy[r], cv.y, __fmaf_rn(qx[r], cv.x, 0.f)));
+                const float t = -2.0f * dot;
+                const float u = __fsub_rn(-cv.w, t);
+                const float pd = __fsub_rn(u, qq[r]);
+                unsigned mask = __ballot_sync(kFull, valid && pd >= tv[r]);   // cheap filter; exact order below
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float cvv = __shfl_sync(kFull, pd, src);
+                    const int cj = __shfl_sync(kFull, j, src);
+                    const bool better = (lv[r] > cvv) || (lv[r] == cvv && li[r] < cj);
+                    const int pos = __popc(__ballot_sync(kFull, better));
+                    if (pos < k) {
+                        const float upv = __shfl_up_sync(kFull, lv[r], 1);
+                        const int upi = __shfl_up_sync(kFull, li[r], 1);
+                        if (lane < k) {
+                            if (lane > pos) { lv[r] = upv; li[r] = upi; }
+                            else if (lane == pos) { lv[r] = cvv; li[r] = cj; }
+                        }
+                        tv[r] = __shfl_sync(kFull, lv[r], k - 1);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KNN3_RPW; ++r) {
+        const int row = row0 + r;
+        if (row < N && lane < k) {
+            const size_t o = ((size_t)b * N + row) * k + lane;
+            if (idx_i64) reinterpret_cast<long long*>(idx_out)[o] = li[r];
+            else reinterpret_cast<int*>(idx_out)[o] = li[r];
+        }
+    }
+}
+
+static int knn3_launch(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, cudaStream_t st) {
+    const size_t smem = (size_t)(N < KNN3_CHUNK ? N : KNN3_CHUNK) * sizeof(float4);
+    LPD_CUDA_CHECK(allow_smem(knn3_kernel, smem > 48 * 1024 ? smem : 48 * 1024));
+    dim3 grid(ceil_div(N, KNN3_ROWS), B);
+    knn3_kernel<<<grid, KNN3_WARPS * 32, smem, st>>>(x, N, C, k, idx, idx_i64);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
 }  // namespace lpd
 
 extern "C" int lpd_knn(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, void* stream) {
@@ -192,6 +292,7 @@ extern "C" int lpd_knn(const float* x, int B, int N, int C, int k, void* idx, in
     LPD_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && C >= 1 && C <= 64);
     LPD_REQUIRE(k >= 1 && k <= 32 && k <= N);
     cudaStream_t st = as_stream(stream);
+    if (C <= 3) return knn3_launch(x, B, N, C, k, idx, idx_i64, st);
     if (C <= 4) return knn_launch<4>(x, B, N, C, k, idx, idx_i64, st);
     if (C <= 8) return knn_launch<8>(x, B, N, C, k, idx, idx_i64, st);
     if (C <= 16) return knn_launch<16>(x, B, N, C, k, idx, idx_i64, st);

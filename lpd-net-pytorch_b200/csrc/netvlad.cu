@@ -106,6 +106,14 @@ extern "C" int lpd_netvlad_assign(const float* x, int M, int D, const float* wc,
     return LPD_OK;
 }
 
+extern "C" int lpd_softmax64(float* a, long long M, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(a && M >= 1);
+    softmax64_kernel<<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(a, M);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
 extern "C" int lpd_netvlad_finish(float* vlad, const float* a, const float* wc2, int B, int N, int D, int K,
                                   float* asum_ws, void* stream) {
     using namespace lpd;

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import (ACT_GATE, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, A_KM, A_MK, B_KN, B_NK)
 
 __all__ = ["bn_fold", "transpose", "knn", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
-           "gemm_tf32", "linear", "set_precision", "get_precision", "netvlad_assign", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
+           "gemm_tf32", "linear", "set_precision", "get_precision", "netvlad_assign", "softmax64", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
            "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ACT_SIGMOID", "ACT_GATE", "A_MK", "A_KM", "B_NK", "B_KN"]
 
 
@@ -192,6 +192,12 @@ def netvlad_assign(x, M, D, wc, scale, shift, K=64, out=None):
     _call("lpd_netvlad_assign", 2, lib.lpd_netvlad_assign, x.data_ptr(), M, D, wc.data_ptr(), _p(scale), _p(shift), K, out.data_ptr(),
                                       _stream())
     return out
+
+
+def softmax64(a, M):
+    lib = _lib.load()
+    _call("lpd_softmax64", 1, lib.lpd_softmax64, a.data_ptr(), M, _stream())
+    return a
 
 
 def netvlad_finish(vlad, a, wc2, B, N, D, K=64):

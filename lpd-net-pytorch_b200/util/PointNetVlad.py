@@ -87,6 +87,7 @@ class NetVLADLoupe(nn.Module):
     def _build(self):
         p = {"wc": self.cluster_weights.detach().contiguous(), "wc2": self.cluster_weights2.detach()[0].contiguous(),
              "wh": self.hidden1_weights.detach().contiguous()}
+        p["wct"] = ops.transpose(p["wc"].unsqueeze(0))[0]      # [K, D]: K-contiguous operand for the tensor-core path
         if self.add_batch_norm:
             p["s1"], p["t1"] = fold_bn(self.bn1)
         else:
@@ -102,7 +103,10 @@ class NetVLADLoupe(nn.Module):
         p = self._prep.get(self, self._build)
         N, D, K, O = self.max_samples, self.feature_size, self.cluster_size, self.output_dim
         M = B * N
-        a = ops.netvlad_assign(f, M, D, p["wc"], p["s1"], p["t1"], K)                         # :48-59
+        if ops.get_precision() == "tf32" and M >= 128 and D % 4 == 0:                         # :48-59
+            a = ops.softmax64(ops.gemm_tf32(f, p["wct"], M=M, N=K, K=D, scale=p["s1"], shift=p["t1"]), M)
+        else:
+            a = ops.netvlad_assign(f, M, D, p["wc"], p["s1"], p["t1"], K)
         vraw = ops.gemm(f, a, a_layout=ops.A_KM, b_layout=ops.B_KN, M=D, N=K, K=N, lda=D, ldb=K, batch=B,
                         strideA=N * D, strideB=N * K)                                         # :64-66 -> [B, D, K]
         if B == 1:
@@ -186,13 +190,13 @@ class STN3d(nn.Module):
                              f"(the reference's MaxPool2d((num_points,1)) silently mis-pools here)")
         p = self._prep.get(self, self._build)
         M, R = B * N, ops.ACT_RELU
-        h = ops.gemm(rows, p["w1"], M=M, N=64, K=self.k, scale=p["s1"], shift=p["t1"], act=R)
-        h = ops.gemm(h, p["w2"], M=M, N=128, K=64, scale=p["s2"], shift=p["t2"], act=R)
-        h = ops.gemm(h, p["w3"], M=M, N=1024, K=128, scale=p["s3"], shift=p["t3"], act=R)
+        h = ops.linear(rows, p["w1"], M=M, N=64, K=self.k, scale=p["s1"], shift=p["t1"], act=R)
+        h = ops.linear(h, p["w2"], M=M, N=128, K=64, scale=p["s2"], shift=p["t2"], act=R)
+        h = ops.linear(h, p["w3"], M=M, N=1024, K=128, scale=p["s3"], shift=p["t3"], act=R)
         g = ops.colmax(h, B, N, 1024)
-        g = ops.gemm(g, p["w4"], M=B, N=512, K=1024, scale=p["s4"], shift=p["t4"], act=R)
-        g = ops.gemm(g, p["w5"], M=B, N=256, K=512, scale=p["s5"], shift=p["t5"], act=R)
-        g = ops.gemm(g, p["w6"], M=B, N=self.k * self.k, K=256, shift=p["t6"])
+        g = ops.linear(g, p["w4"], M=B, N=512, K=1024, scale=p["s4"], shift=p["t4"], act=R)
+        g = ops.linear(g, p["w5"], M=B, N=256, K=512, scale=p["s5"], shift=p["t5"], act=R)
+        g = ops.linear(g, p["w6"], M=B, N=self.k * self.k, K=256, shift=p["t6"])
         return g.view(B, self.k, self.k)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -253,17 +257,17 @@ class PointNetfeat(nn.Module):
         xt = ops.gemm(rows, trans, b_layout=ops.B_KN, M=N, N=3, K=3, lda=3, ldb=3, batch=B,
                       strideA=N * 3, strideB=9, strideC=N * 3,
                       out=torch.empty(M, 3, device=x.device, dtype=torch.float32), ldc=3)     # :209
-        h = ops.gemm(xt, p["w1"], M=M, N=64, K=3, scale=p["s1"], shift=p["t1"], act=R)         # :213
-        h2 = ops.gemm(h, p["w2"], M=M, N=64, K=64, scale=p["s2"], shift=p["t2"], act=R)        # :215
+        h = ops.linear(xt, p["w1"], M=M, N=64, K=3, scale=p["s1"], shift=p["t1"], act=R)         # :213
+        h2 = ops.linear(h, p["w2"], M=M, N=64, K=64, scale=p["s2"], shift=p["t2"], act=R)        # :215
         h = h2
         if self.apply_feature_trans:                                                          # :218-225
             ft = self.feature_trans.forward_pm(h2, B, N)
             h = ops.gemm(h2, ft, b_layout=ops.B_KN, M=N, N=64, K=64, lda=64, ldb=64, batch=B,
                          strideA=N * 64, strideB=64 * 64, strideC=N * 64,
                          out=torch.empty(M, 64, device=x.device, dtype=torch.float32), ldc=64)
-        h = ops.gemm(h, p["w3"], M=M, N=64, K=64, scale=p["s3"], shift=p["t3"], act=R)         # :226
-        h = ops.gemm(h, p["w4"], M=M, N=128, K=64, scale=p["s4"], shift=p["t4"], act=R)        # :228
-        f = ops.gemm(h, p["w5"], M=M, N=self.emb_dims, K=128, scale=p["s5"], shift=p["t5"])    # :230 (no ReLU)
+        h = ops.linear(h, p["w3"], M=M, N=64, K=64, scale=p["s3"], shift=p["t3"], act=R)         # :226
+        h = ops.linear(h, p["w4"], M=M, N=128, K=64, scale=p["s4"], shift=p["t4"], act=R)        # :228
+        f = ops.linear(h, p["w5"], M=M, N=self.emb_dims, K=128, scale=p["s5"], shift=p["t5"])    # :230 (no ReLU)
         return f, trans, h2, B, N
 
     def forward(self, x: torch.Tensor):

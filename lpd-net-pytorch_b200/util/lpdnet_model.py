@@ -136,13 +136,13 @@ class TranformNet(nn.Module):
         training_unsupported(self, "TranformNet")
         p = self._prep.get(self, self._build)
         M, R = B * N, ops.ACT_RELU
-        h = ops.gemm(rows, p["w1"], M=M, N=64, K=self.k, lda=ld, scale=p["s1"], shift=p["t1"], act=R)
-        h = ops.gemm(h, p["w2"], M=M, N=128, K=64, scale=p["s2"], shift=p["t2"], act=R)
-        h = ops.gemm(h, p["w3"], M=M, N=1024, K=128, scale=p["s3"], shift=p["t3"], act=R)
+        h = ops.linear(rows, p["w1"], M=M, N=64, K=self.k, lda=ld, scale=p["s1"], shift=p["t1"], act=R)
+        h = ops.linear(h, p["w2"], M=M, N=128, K=64, scale=p["s2"], shift=p["t2"], act=R)
+        h = ops.linear(h, p["w3"], M=M, N=1024, K=128, scale=p["s3"], shift=p["t3"], act=R)
         g = ops.colmax(h, B, N, 1024)
-        g = ops.gemm(g, p["w4"], M=B, N=512, K=1024, scale=p["s4"], shift=p["t4"], act=R)
-        g = ops.gemm(g, p["w5"], M=B, N=256, K=512, scale=p["s5"], shift=p["t5"], act=R)
-        g = ops.gemm(g, p["w6"], M=B, N=self.k * self.k, K=256, shift=p["t6"])
+        g = ops.linear(g, p["w4"], M=B, N=512, K=1024, scale=p["s4"], shift=p["t4"], act=R)
+        g = ops.linear(g, p["w5"], M=B, N=256, K=512, scale=p["s5"], shift=p["t5"], act=R)
+        g = ops.linear(g, p["w6"], M=B, N=self.k * self.k, K=256, shift=p["t6"])
         return g.view(B, self.k, self.k)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -156,18 +156,24 @@ class _LPDBase(nn.Module):
     """Common forward plumbing of LPDNet / LPDNetOrign."""
 
     def _front(self, x, p, who):
-        """input split, optional T-Nets, conv1/conv2 -> (h2 [M,64], xyz_init [B,N,3], B, N)"""
-        rows, xyz_init, B, N, D = _split_input(x, self.use_mFea, who)
-        M = B * N
-        act, slope = _act_code(self)
-        if self.t3d:
-            trans = self.t_net3d.forward_pm(rows, B, N, D)           # T-Net sees the raw xyz columns
-            rows = _apply_transform(rows, trans, B, N, 3, D)         # kNN below still uses xyz_init (reference :226,:255)
-        h = ops.gemm(rows, p["w1"], M=M, N=64, K=D, scale=p["s1"], shift=p["t1"], act=act, slope=slope)
-        h = ops.gemm(h, p["w2"], M=M, N=64, K=64, scale=p["s2"], shift=p["t2"], act=act, slope=slope)
-        if self.tfea:
-            tf = self.t_net_fea.forward_pm(h, B, N, 64)
-            h = _apply_transform(h, tf, B, N, 64, 64)
+        """input split, optional T-Nets, conv1/conv2 -> (h2 [M,64], xyz_init [B,N,3], B, N).
+        Everything here feeds the feature-space kNN, so it always runs in strict fp32 arithmetic (a TF32-rounded
+        feature would move points across the k-th-neighbour boundary far beyond the few-ulp near-ties)."""
+        prev = ops.set_precision("fp32")
+        try:
+            rows, xyz_init, B, N, D = _split_input(x, self.use_mFea, who)
+            M = B * N
+            act, slope = _act_code(self)
+            if self.t3d:
+                trans = self.t_net3d.forward_pm(rows, B, N, D)           # T-Net sees the raw xyz columns
+                rows = _apply_transform(rows, trans, B, N, 3, D)         # kNN below still uses xyz_init (reference :226,:255)
+            h = ops.linear(rows, p["w1"], M=M, N=64, K=D, scale=p["s1"], shift=p["t1"], act=act, slope=slope)
+            h = ops.linear(h, p["w2"], M=M, N=64, K=64, scale=p["s2"], shift=p["t2"], act=act, slope=slope)
+            if self.tfea:
+                tf = self.t_net_fea.forward_pm(h, B, N, 64)
+                h = _apply_transform(h, tf, B, N, 64, 64)
+        finally:
+            ops.set_precision(prev)
         return h, xyz_init, B, N
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -232,18 +238,18 @@ class LPDNet(_LPDBase):
         dev = h.device
         # feature-space graph: DG1 + DG2 fused, x1 | x2 land in columns 0..255 of the 512-wide pyramid buffer
         idx_f = ops.knn(h.view(B, N, 64), k)
-        pq1 = ops.gemm(h, p["wpq1"], M=M, N=256, K=64)
+        pq1 = ops.linear(h, p["wpq1"], M=M, N=256, K=64)
         pyr = torch.empty(M, 512, device=dev, dtype=torch.float32)
         ops.edgeconv_dg(pq1, 256, pq1[:, 128:], 256, idx_f, B, N, k, 128, 128, p["sdg1"], p["tdg1"], p["wdg2"],
                         p["sdg2"], p["tdg2"], act, slope, pyr, 512, pyr[:, 128:], 512)
         del pq1
         # Cartesian graph on the untransformed input coordinates: SN1 over x2
         idx_x = ops.knn(xyz_init, k)
-        pq3 = ops.gemm(pyr[:, 128:], p["wpq3"], M=M, N=512, K=128, lda=512)
+        pq3 = ops.linear(pyr[:, 128:], p["wpq3"], M=M, N=512, K=128, lda=512)
         ops.edge_gather_ext(pq3, 512, pq3[:, 256:], 512, idx_x, B, N, k, 256, p["ssn1"], p["tsn1"], act, slope,
                             pyr[:, 256:], 512)
         del pq3
-        f = ops.gemm(pyr, p["w3"], M=M, N=self.emb_dims, K=512, scale=p["s3"], shift=p["t3"], act=act, slope=slope)
+        f = ops.linear(pyr, p["w3"], M=M, N=self.emb_dims, K=512, scale=p["s3"], shift=p["t3"], act=act, slope=slope)
         return f, B, N
 
 
@@ -304,17 +310,17 @@ class LPDNetOrign(_LPDBase):
         act, slope = _act_code(self)
         dev = h.device
         idx_f = ops.knn(h.view(B, N, 64), k)
-        pq1 = ops.gemm(h, p["wpq1"], M=M, N=128, K=64)
+        pq1 = ops.linear(h, p["wpq1"], M=M, N=128, K=64)
         xdg = torch.empty(M, 64, device=dev, dtype=torch.float32)
         ops.edgeconv_dg(pq1, 128, pq1[:, 64:], 128, idx_f, B, N, k, 64, 64, p["sdg1"], p["tdg1"], p["wdg2"],
                         p["sdg2"], p["tdg2"], act, slope, None, 0, xdg, 64)
         # gather-only edges: SN1 and SN2 act on each neighbour independently -> evaluate them per POINT, then max-gather
         idx_x = ops.knn(xyz_init, k)
-        g = ops.gemm(xdg, p["wsn1"], M=M, N=64, K=64, scale=p["ssn1"], shift=p["tsn1"], act=act, slope=slope)
-        g = ops.gemm(g, p["wsn2"], M=M, N=64, K=64, scale=p["ssn2"], shift=p["tsn2"], act=act, slope=slope)
+        g = ops.linear(xdg, p["wsn1"], M=M, N=64, K=64, scale=p["ssn1"], shift=p["tsn1"], act=act, slope=slope)
+        g = ops.linear(g, p["wsn2"], M=M, N=64, K=64, scale=p["ssn2"], shift=p["tsn2"], act=act, slope=slope)
         xsn = torch.empty(M, 64, device=dev, dtype=torch.float32)
         ops.edge_gather_ext(g, 64, None, 0, idx_x, B, N, k, 64, None, None, ops.ACT_NONE, 0.0, xsn, 64)
-        f = ops.gemm(xsn, p["w3"], M=M, N=64, K=64, scale=p["s3"], shift=p["t3"], act=act, slope=slope)
-        f = ops.gemm(f, p["w4"], M=M, N=128, K=64, scale=p["s4"], shift=p["t4"], act=act, slope=slope)
-        f = ops.gemm(f, p["w5"], M=M, N=self.emb_dims, K=128, scale=p["s5"], shift=p["t5"], act=act, slope=slope)
+        f = ops.linear(xsn, p["w3"], M=M, N=64, K=64, scale=p["s3"], shift=p["t3"], act=act, slope=slope)
+        f = ops.linear(f, p["w4"], M=M, N=128, K=64, scale=p["s4"], shift=p["t4"], act=act, slope=slope)
+        f = ops.linear(f, p["w5"], M=M, N=self.emb_dims, K=128, scale=p["s5"], shift=p["t5"], act=act, slope=slope)
         return f, B, N

@@ -157,3 +157,31 @@ def test_get_latent_vectors_batches_and_tail(cuda, golden):
     got = evaluate.get_latent_vectors(model, x[:, 0].numpy(), batch_num=3)
     assert got.shape == (7, 256) and np.array_equal(got, want)
     assert not model.training
+
+
+# ------------------------------------------------------------------------------------------------ TF32 (tensor-core) mode
+TF32_TOL = 2e-4   # stated looser bound for the tcgen05 kind::tf32 path (north_star allows one); measured values are printed
+
+
+@pytest.mark.parametrize("name,B,N,kw", [
+    ("c1_pointnet_eval", 2, 4096, dict(featnet="pointnet")),
+    ("c2_lpdnet_eval", 4, 4096, dict(featnet="lpdnet")),
+    ("c2_lpdnet_tnets_eval", 2, 1024, dict(featnet="lpdnet", feature_transform=True, xyz_trans=True)),
+    ("c2_lpdnetorigin_eval", 2, 4096, dict(featnet="lpdnetorigin")),
+])
+def test_tf32_mode_descriptor_error_bound(cuda, golden, name, B, N, kw):
+    g = golden(name)
+    model, _ = build(g, num_points=N, emb_dims=1024, **kw)
+    x = synth.clouds(B, N).cuda()
+    prev = ops.set_precision("tf32")
+    try:
+        ops.profile(True)
+        with torch.no_grad():
+            out = model(x).cpu().numpy()
+        labels = [r[0] for r in ops.profile(False)]
+    finally:
+        ops.set_precision(prev)
+    assert any(l.startswith("lpd_gemm_tf32") for l in labels), "tensor-core path was not taken"
+    err = np.abs(out - g["out"]).max()
+    print(f"\n[tf32] {name}: max-abs descriptor error {err:.3e} (|out|max {np.abs(g['out']).max():.3f})")
+    assert err <= TF32_TOL, f"{name}: {err:.3e}"
