@@ -49,11 +49,14 @@ def kernel_work(label: str, B: int):
     if label.startswith("lpd_gemm["):
         M, Nn, K, batch = (int(v) for v in label[9:-1].split("x"))
         return 2.0 * M * Nn * K * batch, 4.0 * batch * (M * K + Nn * K + M * Nn)
+    if label.startswith("lpd_gemm_tf32["):
+        M, Nn, K = (int(v) for v in label[14:-1].split("x"))
+        return 2.0 * M * Nn * K, 4.0 * (M * K + Nn * K + M * Nn)
     if label.startswith("lpd_knn[C=64"):
         return 2.0 * N * N * 64 * B, 4.0 * B * N * (64 + k)
     if label.startswith("lpd_knn[C=3"):
         return 2.0 * N * N * 3 * B, 4.0 * B * N * (3 + k)
-    if label.startswith("lpd_edgeconv_dg[128"):
+    if label.startswith("lpd_edgeconv_dg[128") or label.startswith("lpd_edgeconv_dg_tf32[128"):
         return 2.0 * N * k * 128 * 128 * B, 4.0 * B * N * (256 + 256 + k)
     if label.startswith("lpd_edge_gather_ext"):
         C = int(label.split("C=")[1].rstrip("]"))
@@ -189,6 +192,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    ops.set_precision(args.precision)
     model, _ = build_model(device)
     # per-rank shard of the synthetic submap stream: 4 distinct batches so consecutive steps never see the same input
     n_rot = 4
@@ -271,15 +275,18 @@ def run_ours(args):
             roofline = {"kernel": top, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained",
                         "share_of_step": tot[top] / step_ms, "ms_per_launch": per_launch_ms,
-                        "note": "fp32 FFMA (CUDA-core) kernel graded against the dense bf16 tensor peak; algorithmic FLOPs per launch"}
+                        "note": "algorithmic FLOPs per launch / CUDA-event time, graded against the dense bf16 tensor peak "
+                                "(TF32 tensor-core or fp32 CUDA-core kernel: its own peak is 1/2 resp. ~1/20 of that)"}
 
     if rank == 0:
         threads = os.cpu_count() or 1
         cpu_v, cpu_t = cpu_baseline(threads, threads)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "C2: LPD-Net eval embedding (featnet=lpdnet, kNN k=20 graph features + NetVLAD K=64 D=1024 -> 256)",
+                "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+                "config": {"precision": ("tf32 tensor-core GEMMs (fp32 storage, fp32 accumulate; kNN and its input layers exact fp32)"
+                                         if args.precision == "tf32" else "strict fp32 FFMA"),
+                           "workload": "C2: LPD-Net eval embedding (featnet=lpdnet, kNN k=20 graph features + NetVLAD K=64 D=1024 -> 256)",
                            "submaps_per_gpu_per_step": BATCH, "points": NPTS, "sharding": f"batch-sharded dp{world}, no collective",
                            "l2": "256 MiB memset between timed steps (untimed); 4 rotating input batches; intermediates > 1 GiB/step"},
                 "clocks": clk.result, "gpu_launches": launches,
@@ -300,6 +307,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
+                    help="tf32: dense layers on tcgen05 tensor cores (descriptor error vs the reference measured <= 1e-4); "
+                         "fp32: every layer in strict fp32 FFMA arithmetic")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

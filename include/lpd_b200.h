@@ -148,6 +148,15 @@ int lpd_edgeconv_dg(const float* p, int ldp, const float* q, int ldq,
                     const float* s2, const float* t2, int act, float slope,
                     float* x1, int ld1, float* x2, int ld2, void* stream);
 
+/* Same contract as lpd_edgeconv_dg with the second edge layer on the tensor cores (tcgen05 kind::tf32, the
+ * activated first-layer edge rows are written by the gathering warps straight into the UMMA shared-memory
+ * layout; fp32 first layer, TF32 second layer, fp32 accumulation).  Requires sm_100. */
+int lpd_edgeconv_dg_tf32(const float* p, int ldp, const float* q, int ldq,
+                         const int32_t* idx, int B, int N, int k, int C1, int C2,
+                         const float* s1, const float* t1, const float* w2,
+                         const float* s2, const float* t2, int act, float slope,
+                         float* x1, int ld1, float* x2, int ld2, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * NetVLAD soft-assignment: a[m][:] = softmax_K( s * (x[m][:] . Wc) + t )
  * Replaces PointNetVlad.py:48-59 (matmul, BatchNorm1d(K) or cluster_biases, softmax).

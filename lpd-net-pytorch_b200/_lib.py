@@ -37,6 +37,8 @@ SIGNATURES = {
     "lpd_edge_gather_ext": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _i, _vp]),
     "lpd_edgeconv_dg": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f,
                              _vp, _i, _vp, _i, _vp]),
+    "lpd_edgeconv_dg_tf32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f,
+                                  _vp, _i, _vp, _i, _vp]),
     "lpd_netvlad_assign": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "lpd_softmax64": (_i, [_vp, _ll, _vp]),
     "lpd_netvlad_finish": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -178,10 +178,13 @@ def edge_gather_ext(p, ldp, q, ldq, idx, B, N, k, C, scale, shift, act, slope, o
 
 
 def edgeconv_dg(p, ldp, q, ldq, idx, B, N, k, C1, C2, s1, t1, w2, s2, t2, act, slope, x1, ld1, x2, ld2):
+    """Two fused edge layers (see lpd_edgeconv_dg); second layer on the tensor cores in "tf32" precision mode."""
     lib = _lib.load()
-    _call(f"lpd_edgeconv_dg[{C1}x{C2}]", 1, lib.lpd_edgeconv_dg, p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), B, N, k, C1, C2,
-                                   s1.data_ptr(), t1.data_ptr(), w2.data_ptr(), s2.data_ptr(), t2.data_ptr(),
-                                   act, float(slope), _p(x1), ld1, x2.data_ptr(), ld2, _stream())
+    tf32 = _precision == "tf32" and act != ACT_SIGMOID
+    fn, label = (lib.lpd_edgeconv_dg_tf32, "lpd_edgeconv_dg_tf32") if tf32 else (lib.lpd_edgeconv_dg, "lpd_edgeconv_dg")
+    _call(f"{label}[{C1}x{C2}]", 1, fn, p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), B, N, k, C1, C2,
+          s1.data_ptr(), t1.data_ptr(), w2.data_ptr(), s2.data_ptr(), t2.data_ptr(),
+          act, float(slope), _p(x1), ld1, x2.data_ptr(), ld2, _stream())
     return x1, x2
 
 

@@ -252,3 +252,29 @@ def test_gemm_tf32_tensor_core_path(cuda, M, N, K, ldx):
     # and it agrees with the strict fp32 path to TF32 accuracy
     strict = ops.gemm(dev(A), dev(W), M=M, N=N, K=K, lda=lda, scale=dev(scale), shift=dev(shift), act=ops.ACT_LEAKY, slope=0.01)
     assert np.abs(strict.cpu().numpy() - got[:, 32:32 + N]).max() < 2.0 ** -9 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("B,N,k,C", [(2, 300, 20, 128), (1, 257, 32, 128), (1, 100, 7, 128), (2, 200, 20, 64), (1, 90, 25, 64), (3, 1024, 20, 128)])
+def test_edgeconv_dg_tensor_core_path(cuda, B, N, k, C):
+    """lpd_edgeconv_dg_tf32: first layer exact fp32, second layer TF32 on tcgen05 -> 2^-9 of the layer-2 scale"""
+    r = rng(N + k + C + 1)
+    pq = r.standard_normal((B * N, 2 * C)).astype(np.float32)
+    idx = r.integers(0, N, (B, N, k)).astype(np.int32)
+    s1, t1, s2, t2 = (r.standard_normal(C).astype(np.float32) for _ in range(4))
+    w2 = (r.standard_normal((C, C)) / np.sqrt(C)).astype(np.float32)
+    P, Q = pq[:, :C].reshape(B, N, C), pq[:, C:].reshape(B, N, C)
+    y1 = _leaky((P[np.arange(B)[:, None, None], idx] + Q[:, :, None, :]).astype(np.float64) * s1 + t1)
+    y2 = _leaky((y1 @ w2.astype(np.float64).T) * s2 + t2)
+    x1_ref, x2_ref = y1.max(2).reshape(B * N, C), y2.max(2).reshape(B * N, C)
+    d_pq = dev(pq)
+    x = torch.zeros(B * N, 2 * C, device="cuda")
+    prev = ops.set_precision("tf32")
+    try:
+        ops.edgeconv_dg(d_pq, 2 * C, d_pq[:, C:], 2 * C, dev(idx, torch.int32), B, N, k, C, C, dev(s1), dev(t1), dev(w2), dev(s2), dev(t2),
+                        ops.ACT_LEAKY, 0.01, x, 2 * C, x[:, C:], 2 * C)
+    finally:
+        ops.set_precision(prev)
+    got = x.cpu().numpy()
+    assert np.abs(got[:, :C] - x1_ref).max() < 1e-5
+    scale2 = np.abs(y2).max()
+    assert np.abs(got[:, C:] - x2_ref).max() < 2.0 ** -8 * scale2
