@@ -52,7 +52,7 @@ def kernel_work(label: str, B: int):
     if label.startswith("lpd_gemm_tf32["):
         M, Nn, K = (int(v) for v in label[14:-1].split("x"))
         return 2.0 * M * Nn * K, 4.0 * (M * K + Nn * K + M * Nn)
-    if label.startswith("lpd_knn[C=64"):
+    if label.startswith("lpd_knn[C=64") or label.startswith("lpd_knn_tc[C=64"):
         return 2.0 * N * N * 64 * B, 4.0 * B * N * (64 + k)
     if label.startswith("lpd_knn[C=3"):
         return 2.0 * N * N * 3 * B, 4.0 * B * N * (3 + k)

@@ -88,6 +88,14 @@ int lpd_transpose(const float* in, float* out, int batch, int rows, int cols, vo
  * ------------------------------------------------------------------------------------------- */
 int lpd_knn(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, void* stream);
 
+/* Same result as lpd_knn (bit-identical canonical order) for C == 64, with the distance GEMM on the tensor cores:
+ * TF32 gram tiles (tcgen05) filter candidates, the survivors are re-scored in canonical fp32 arithmetic, and rows whose
+ * candidate list cannot be proven complete fall back to the CUDA-core kernel.  `workspace`: device scratch of at least
+ * lpd_knn_workspace_bytes(B, N, C, k) bytes, 16-byte aligned.  Requires sm_100. */
+size_t lpd_knn_workspace_bytes(int B, int N, int C, int k);
+int lpd_knn_tc(const float* x, int B, int N, int C, int k, void* idx, int idx_i64,
+               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * General fp32 GEMM with fused per-column affine + activation epilogue (CUDA-core FFMA path,
  * "strict" fp32 arithmetic):

@@ -30,6 +30,8 @@ SIGNATURES = {
     "lpd_bn_fold": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     "lpd_transpose": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "lpd_knn": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "lpd_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "lpd_knn_tc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "lpd_gemm": (_i, [_vp, _i, _i, _ll, _vp, _i, _i, _ll, _vp, _i, _ll, _i, _i, _i, _i,
                       _vp, _vp, _i, _f, _vp, _vp]),
     "lpd_gemm_tf32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp]),

@@ -64,7 +64,10 @@ __device__ __forceinline__ float knn_sqnorm(const float* __restrict__ t, int p) 
 
 template <int CP>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
-knn_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ idx_out, int idx_i64) {
+knn_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ idx_out, int idx_i64,
+           const int* __restrict__ tile_flags) {
+    // fallback mode of the tensor-core path: only 64-row tiles flagged as "needs exact recompute" do any work
+    if (tile_flags != nullptr && tile_flags[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;
     extern __shared__ __align__(16) float smem[];
     float* Qs = smem;                      // [CP][QT]
     float* Cs = Qs + CP * KNN_QT;          // [CP][CT]
@@ -175,11 +178,12 @@ knn_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ 
 }
 
 template <int CP>
-static int knn_launch(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, cudaStream_t st) {
+static int knn_launch(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, cudaStream_t st,
+                      const int* tile_flags = nullptr) {
     const size_t smem = (size_t)(CP * (KNN_QT + KNN_CT) + KNN_QT * KNN_CT + KNN_QT + KNN_CT) * sizeof(float);
     LPD_CUDA_CHECK(allow_smem(knn_kernel<CP>, smem));
     dim3 grid(ceil_div(N, KNN_QT), B);
-    knn_kernel<CP><<<grid, KNN_THREADS, smem, st>>>(x, N, C, k, idx, idx_i64);
+    knn_kernel<CP><<<grid, KNN_THREADS, smem, st>>>(x, N, C, k, idx, idx_i64, tile_flags);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }
@@ -273,6 +277,10 @@ knn3_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__
             else reinterpret_cast<int*>(idx_out)[o] = li[r];
         }
     }
+}
+
+int knn_simt64_flagged(const float* x, int B, int N, int k, void* idx, int idx_i64, const int* flags, cudaStream_t st) {
+    return knn_launch<64>(x, B, N, 64, k, idx, idx_i64, st, flags);
 }
 
 static int knn3_launch(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, cudaStream_t st) {

@@ -278,3 +278,37 @@ def test_edgeconv_dg_tensor_core_path(cuda, B, N, k, C):
     assert np.abs(got[:, :C] - x1_ref).max() < 1e-5
     scale2 = np.abs(y2).max()
     assert np.abs(got[:, C:] - x2_ref).max() < 2.0 ** -8 * scale2
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core kNN (exact)
+@pytest.mark.parametrize("B,N,k,kind", [
+    (2, 512, 20, "relu"), (3, 130, 20, "relu"), (1, 2048, 32, "relu"), (2, 1000, 24, "relu"), (2, 1000, 25, "relu"),
+    (1, 4096, 20, "relu"), (1, 300, 20, "dups"), (1, 256, 20, "same"), (1, 640, 20, "big"), (1, 128, 1, "relu"),
+    (2, 700, 20, "clusters"),
+])
+def test_knn_tensor_core_filter_refine_is_bit_exact(cuda, B, N, k, kind):
+    """lpd_knn_tc must return exactly the canonical neighbour lists, including on inputs built to defeat the TF32 filter
+    (duplicates, all-identical points, huge norms, tight clusters) where rows fall back to the exact kernel."""
+    r = rng(N + k)
+    x = np.maximum(r.standard_normal((B, N, 64)), 0.01 * r.standard_normal((B, N, 64))).astype(np.float32)
+    if kind == "dups":
+        x[:, 100:200] = x[:, 0:100]
+    elif kind == "same":
+        x[:] = x[:, :1]
+    elif kind == "big":
+        x = (x * 300 + 1000).astype(np.float32)
+    elif kind == "clusters":
+        centres = r.standard_normal((B, 7, 64)).astype(np.float32) * 3
+        x = (centres[:, r.integers(0, 7, N)] + 1e-3 * r.standard_normal((B, N, 64))).astype(np.float32)
+    want = knn_canonical(x, k)
+    prev, ops.KNN_TENSOR_CORES = ops.KNN_TENSOR_CORES, True
+    try:
+        ops.profile(True)
+        got = ops.knn(dev(x), k).cpu().numpy()
+        labels = [l for l, _, _ in ops.profile(False)]
+    finally:
+        ops.KNN_TENSOR_CORES = prev
+    assert labels and labels[0].startswith("lpd_knn_tc")
+    assert np.array_equal(got, want)
+    assert not ops.KNN_TENSOR_CORES
+    assert np.array_equal(ops.knn(dev(x), k).cpu().numpy(), want)      # default CUDA-core kernel, same bits
