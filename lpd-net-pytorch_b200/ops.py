@@ -87,10 +87,9 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-# C == 64 only: exact filter-and-refine kNN with the gram tiles on tcgen05 (lpd_knn_tc).  Bit-identical results, but
-# measured slower than the CUDA-core kernel on the C2 workload in this round (selection is latency-bound on the four
-# TMEM-attached warps and the single-pass TF32 margin sends most rows to the exact fallback) -> opt-in, see DESIGN.md.
-KNN_TENSOR_CORES = False
+# C == 64: exact filter-and-refine kNN with the gram tiles on tcgen05 (lpd_knn_tc, 3xTF32 + canonical re-score).
+# Bit-identical to the CUDA-core kernel; rows whose candidate list cannot be proven complete are recomputed by it.
+KNN_TENSOR_CORES = True
 
 
 def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
@@ -100,10 +99,10 @@ def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
     x_pm = _f32(x_pm, "x").contiguous()
     B, N, Cc = x_pm.shape
     idx = torch.empty(B, N, k, device=x_pm.device, dtype=torch.int64 if int64 else torch.int32)
-    if KNN_TENSOR_CORES and Cc == 64 and N >= 128:
+    if KNN_TENSOR_CORES and Cc == 64 and N >= 128 and x_pm.data_ptr() % 16 == 0:
         nbytes = lib.lpd_knn_workspace_bytes(B, N, Cc, k)
-        ws = torch.empty((nbytes + 15) // 16 * 4, device=x_pm.device, dtype=torch.float32)
-        _call(f"lpd_knn_tc[C={Cc},k={k}]", 3, lib.lpd_knn_tc, x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64),
+        ws = torch.empty((nbytes + 3) // 4, device=x_pm.device, dtype=torch.float32)
+        _call(f"lpd_knn_tc[C={Cc},k={k}]", 4, lib.lpd_knn_tc, x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64),
               ws.data_ptr(), ws.numel() * 4, _stream())
     else:
         _call(f"lpd_knn[C={Cc},k={k}]", 1, lib.lpd_knn, x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64), _stream())

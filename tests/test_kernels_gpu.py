@@ -301,14 +301,16 @@ def test_knn_tensor_core_filter_refine_is_bit_exact(cuda, B, N, k, kind):
         centres = r.standard_normal((B, 7, 64)).astype(np.float32) * 3
         x = (centres[:, r.integers(0, 7, N)] + 1e-3 * r.standard_normal((B, N, 64))).astype(np.float32)
     want = knn_canonical(x, k)
-    prev, ops.KNN_TENSOR_CORES = ops.KNN_TENSOR_CORES, True
+    prev = ops.KNN_TENSOR_CORES
     try:
+        ops.KNN_TENSOR_CORES = True
         ops.profile(True)
         got = ops.knn(dev(x), k).cpu().numpy()
         labels = [l for l, _, _ in ops.profile(False)]
+        ops.KNN_TENSOR_CORES = False
+        got_simt = ops.knn(dev(x), k).cpu().numpy()                    # CUDA-core kernel, same bits
     finally:
         ops.KNN_TENSOR_CORES = prev
     assert labels and labels[0].startswith("lpd_knn_tc")
     assert np.array_equal(got, want)
-    assert not ops.KNN_TENSOR_CORES
-    assert np.array_equal(ops.knn(dev(x), k).cpu().numpy(), want)      # default CUDA-core kernel, same bits
+    assert np.array_equal(got_simt, want)
