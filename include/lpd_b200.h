@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LPD_ABI_VERSION 1
+#define LPD_ABI_VERSION 2
 
 typedef enum lpd_status {
     LPD_OK = 0,
@@ -44,7 +44,8 @@ typedef enum lpd_act {
     LPD_ACT_RELU = 1,      /* F.relu, PointNetVlad.py:156-167, lpdnet_model.py:297-303 */
     LPD_ACT_LEAKY = 2,     /* nn.LeakyReLU(slope), lpdnet_model.py:24,153             */
     LPD_ACT_SIGMOID = 3,   /* nn.Sigmoid, PointNetVlad.py:111                          */
-    LPD_ACT_GATE = 4       /* out = aux * sigmoid(v): GatingContext, PointNetVlad.py:111-113 */
+    LPD_ACT_GATE = 4,      /* out = aux * sigmoid(v): GatingContext, PointNetVlad.py:111-113 */
+    LPD_ACT_ADD = 5        /* lpd_gemm only: out = v + aux (aux may alias the output: gradient accumulation) */
 } lpd_act;
 
 /* operand layouts of lpd_gemm */
@@ -217,6 +218,86 @@ size_t lpd_retrieval_workspace_bytes(int Ndb, int Nq, int k);
 int lpd_retrieval_topk(const float* db, int Ndb, const float* q, int Nq, int D, int k,
                        int idx_offset, int32_t* idx, double* dist,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* =============================================================================================
+ * TRAIN MODE (reference: model.train() forward, loss.backward(), optimizer.step();
+ * train_pointnetvlad.py:121-130,150-159).  Batch-statistics BatchNorm and the backward pass.
+ * A "bn" block is 4 consecutive float rows of C: scale = gamma*invstd, shift = beta - mean*scale,
+ * mean, invstd  (what lpd_bn_finalize writes and the backward kernels read).
+ * "partial" buffers are double [nparts][2][C] per-block partial sums (deterministic two-stage reduce).
+ * ============================================================================================= */
+
+/* column sums of z and z^2 over rows -> partial.  nn.BatchNorm{1,2}d batch statistics (torch batch_norm, training=True)
+ * of lpdnet_model.py:168-173,189-191,231-262 and PointNetVlad.py:33,39,97.  C % 4 == 0, ld % 4 == 0. */
+int lpd_bn_stats(const float* z, long long rows, int C, int ld, double* partial, int nparts, void* stream);
+/* partial -> bn block [4][C]; updates running_mean / running_var in place (nullable) with `momentum` and the unbiased
+ * variance, as torch does.  `count` = number of values per channel. */
+int lpd_bn_finalize(const double* partial, int nparts, double count, int C, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var, float* bn_out, void* stream);
+/* out[i] = (float) sum_p partial[p][i], i < n  (n = 2*C for a partial buffer: [S1 | S2]) */
+int lpd_colsum_finalize(const double* partial, int nparts, int n, float* out, void* stream);
+/* out = act(scale * z + shift) elementwise over [rows][C]; LPD_ACT_GATE: out = aux * sigmoid(scale*z+shift). */
+int lpd_affine_act(const float* z, long long rows, int C, int ldz, const float* scale, const float* shift, int act,
+                   float slope, const float* aux, int ldaux, float* out, int ldo, void* stream);
+/* backward of  y = act(BN_batch(z)):  dzbn = dy * act'(scale*z+shift);
+ *   reduce: partial of S1 = sum dzbn (= d beta), S2 = sum dzbn * xhat (= d gamma)
+ *   apply : dz = scale * (dzbn - S1/count - xhat * S2/count)          (S = float [2][C]; dz may alias dy) */
+int lpd_bn_bwd_reduce(const float* dy, int lddy, const float* z, int ldz, long long rows, int C, const float* bn,
+                      int act, float slope, const float* aux, int ldaux, double* partial, int nparts, void* stream);
+int lpd_bn_bwd_apply(const float* dy, int lddy, const float* z, int ldz, long long rows, int C, const float* bn,
+                     const float* S, double count, int act, float slope, const float* aux, int ldaux,
+                     float* dz, int lddz, void* stream);
+
+/* Train-mode EdgeConv (get_graph_feature + Conv2d + BatchNorm2d(batch stats) + act + max, lpdnet_model.py:246-258).
+ * Edge pre-activation z[(i,m)][c] = p[j(i,m)][c] + q[i][c] (q nullable).  BN and the activation are monotone per channel,
+ * so max_m act(BN(z)) = act(BN(zsel)), zsel = q + (gamma >= 0 ? max : min)_m p_j:
+ *   lpd_edge_sel_stats : zsel [M][ldz], arg uint8 [M][C] (first m reaching the extremum), partial of (sum z, sum z^2)
+ *                        over all M*k edges (closed form per point)
+ *   lpd_edge_materialize: y[(i,m)][:] = act(scale*(p_j+q_i)+shift), dense [M*k][C] (input of a following edge layer)
+ *   lpd_edge_sel_dense : the same selection over an already materialised z [M][k][C] */
+int lpd_edge_sel_stats(const float* p, int ldp, const float* q, int ldq, const int32_t* idx, int B, int N, int k, int C,
+                       const float* gamma, float* zsel, int ldz, uint8_t* arg, double* partial, int nparts, void* stream);
+int lpd_edge_materialize(const float* p, int ldp, const float* q, int ldq, const int32_t* idx, int B, int N, int k, int C,
+                         const float* scale, const float* shift, int act, float slope, float* y, void* stream);
+int lpd_edge_sel_dense(const float* z, long long M, int k, int C, const float* gamma, float* zsel, int ldz,
+                       uint8_t* arg, void* stream);
+/* backward of a materialised edge layer whose only consumer is the max over m:
+ *   dz[(i,m)][c] = scale * ([m == arg[i][c]] * dx[i][c] * act'(scale*zsel+shift) - S1/count - xhat(z) * S2/count)
+ * (S from lpd_bn_bwd_reduce over the [M][C] arrays dx / zsel; dz may alias z) */
+int lpd_edge_dense_bwd_apply(const float* z, long long M, int k, int C, const float* bn, const float* S, double count,
+                             int act, float slope, const float* dx, int lddx, const float* zsel, int ldzs,
+                             const uint8_t* arg, float* dz, void* stream);
+/* backward of a decomposed edge layer: incoming gradient = dense dy [(i,m)][C] (nullable) + dx [M][lddx] routed to arg
+ * (nullable).  reduce -> partial (S1, S2); apply -> dq[i] = sum_m dz, dp[j] += dz (fp32 atomics; dp's C columns are zeroed
+ * first) — the index_put_(accumulate=True) of the reference's autograd. */
+int lpd_edge_bwd_reduce(const float* p, int ldp, const float* q, int ldq, const int32_t* idx, int B, int N, int k, int C,
+                        const float* bn, int act, float slope, const float* dx, int lddx, const uint8_t* arg,
+                        const float* dy, double* partial, int nparts, void* stream);
+int lpd_edge_bwd_apply(const float* p, int ldp, const float* q, int ldq, const int32_t* idx, int B, int N, int k, int C,
+                       const float* bn, int act, float slope, const float* dx, int lddx, const uint8_t* arg,
+                       const float* dy, const float* S, double count, float* dp, int lddp, float* dq, int lddq,
+                       void* stream);
+
+/* NetVLAD train mode: lpd_netvlad_finish that also saves asum [B][K], the clamped intra norms n1 [B][K] and the clamped
+ * global norm n2 [B]; its backward (in place on dv [B][D][K] -> d vraw; dasum [B][K]; dwc2 [D][K]); softmax backward
+ * with the a_sum gradient folded in (in place on da [M][64]).  PointNetVlad.py:58-74. */
+int lpd_netvlad_finish_train(float* vlad, const float* a, const float* wc2, int B, int N, int D, int K,
+                             float* asum, float* n1, float* n2, void* stream);
+int lpd_netvlad_finish_bwd(float* dv, const float* v, const float* wc2, const float* asum, const float* n1,
+                           const float* n2, int B, int D, int K, float* dasum, float* dwc2, void* stream);
+int lpd_softmax64_bwd(float* da, const float* a, const float* dasum, long long M, int N, void* stream);
+
+/* column max over the points of each cloud with argmax, and its backward (dx[b][arg][c] += dout[b][c]).
+ * torch.max(x, 2) lpdnet_model.py:300 ; MaxPool2d((num_points,1)) PointNetVlad.py:137,169. */
+int lpd_colmax_arg(const float* x, int B, int N, int C, int ldx, float* out, int32_t* arg, void* stream);
+int lpd_colmax_bwd(const float* dout, const int32_t* arg, int B, int N, int C, float* dx, int lddx, void* stream);
+
+/* torch.optim.Adam step (train_pointnetvlad.py:57,130,159) over a flat parameter buffer; g is multiplied by grad_scale
+ * first (1/world_size after a gradient all-reduce-sum).  step >= 1. */
+int lpd_adam(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+             float weight_decay, int step, float grad_scale, void* stream);
+/* y[r][c] += alpha * x[r][c] */
+int lpd_axpy(float* y, int ldy, const float* x, int ldx, long long rows, int C, float alpha, void* stream);
 
 #ifdef __cplusplus
 }

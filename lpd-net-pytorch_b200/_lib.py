@@ -14,12 +14,12 @@ LIB_PATH = _HERE / "liblpd_b200.so"
 
 # status codes / enums mirrored from include/lpd_b200.h
 LPD_OK = 0
-ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_GATE = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_GATE, ACT_ADD = 0, 1, 2, 3, 4, 5
 A_MK, A_KM = 0, 1
 B_NK, B_KN = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
-_vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
+_vp, _i, _f, _ll, _sz, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes); every symbol include/lpd_b200.h declares
 SIGNATURES = {
@@ -48,6 +48,27 @@ SIGNATURES = {
     "lpd_quadruplet_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lpd_retrieval_workspace_bytes": (_sz, [_i, _i, _i]),
     "lpd_retrieval_topk": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    # ---- train mode ----
+    "lpd_bn_stats": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp]),
+    "lpd_bn_finalize": (_i, [_vp, _i, _d, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "lpd_colsum_finalize": (_i, [_vp, _i, _i, _vp, _vp]),
+    "lpd_affine_act": (_i, [_vp, _ll, _i, _i, _vp, _vp, _i, _f, _vp, _i, _vp, _i, _vp]),
+    "lpd_bn_bwd_reduce": (_i, [_vp, _i, _vp, _i, _ll, _i, _vp, _i, _f, _vp, _i, _vp, _i, _vp]),
+    "lpd_bn_bwd_apply": (_i, [_vp, _i, _vp, _i, _ll, _i, _vp, _vp, _d, _i, _f, _vp, _i, _vp, _i, _vp]),
+    "lpd_edge_sel_stats": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "lpd_edge_materialize": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp]),
+    "lpd_edge_sel_dense": (_i, [_vp, _ll, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "lpd_edge_dense_bwd_apply": (_i, [_vp, _ll, _i, _i, _vp, _vp, _d, _i, _f, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "lpd_edge_bwd_reduce": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "lpd_edge_bwd_apply": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _i, _vp, _vp, _vp, _d,
+                                _vp, _i, _vp, _i, _vp]),
+    "lpd_netvlad_finish_train": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "lpd_netvlad_finish_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "lpd_softmax64_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "lpd_colmax_arg": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lpd_colmax_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "lpd_adam": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "lpd_axpy": (_i, [_vp, _i, _vp, _i, _ll, _i, _f, _vp]),
 }
 
 _lib = None

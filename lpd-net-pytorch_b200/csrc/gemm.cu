@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_kernel(GemmParams p) {
                     if (p.scale) o *= __ldg(p.scale + n + j);
                     if (p.shift) o += __ldg(p.shift + n + j);
                     if (p.act == LPD_ACT_GATE) o = __ldg(p.aux + (size_t)blockIdx.z * p.sC + (size_t)m * p.ldc + n + j) * (1.f / (1.f + expf(-o)));
+                    else if (p.act == LPD_ACT_ADD) o += p.aux[(size_t)blockIdx.z * p.sC + (size_t)m * p.ldc + n + j];  // aux may alias C
                     else o = apply_act(o, p.act, p.slope);
                 }
                 v[j] = o;
@@ -213,8 +214,8 @@ extern "C" int lpd_gemm(const float* A, int a_layout, int lda, long long strideA
     LPD_REQUIRE(lda >= (a_layout == LPD_A_MK ? K : M));
     LPD_REQUIRE(ldb >= (b_layout == LPD_B_NK ? K : N));
     LPD_REQUIRE(ldc >= N);
-    LPD_REQUIRE(act >= LPD_ACT_NONE && act <= LPD_ACT_GATE);
-    LPD_REQUIRE(act != LPD_ACT_GATE || aux != nullptr);
+    LPD_REQUIRE(act >= LPD_ACT_NONE && act <= LPD_ACT_ADD);
+    LPD_REQUIRE((act != LPD_ACT_GATE && act != LPD_ACT_ADD) || aux != nullptr);
     GemmParams p;
     p.A = A; p.B = B; p.C = C; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.sA = strideA; p.sB = strideB; p.sC = strideC; p.M = M; p.N = N; p.K = K;

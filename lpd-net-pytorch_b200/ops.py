@@ -8,7 +8,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import (ACT_GATE, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, A_KM, A_MK, B_KN, B_NK)
+from ._lib import (ACT_ADD, ACT_GATE, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, A_KM, A_MK, B_KN, B_NK)
 
 __all__ = ["bn_fold", "transpose", "knn", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
            "gemm_tf32", "linear", "set_precision", "get_precision", "netvlad_assign", "softmax64", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
@@ -263,3 +263,208 @@ def retrieval_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_offset: int = 
     _call("lpd_retrieval_topk", 2, lib.lpd_retrieval_topk, db.data_ptr(), Ndb, q.data_ptr(), Nq, D, k, idx_offset, idx.data_ptr(), _p(dist),
                                       ws.data_ptr(), ws.numel() * 8, _stream())
     return idx, dist
+
+
+# =====================================================================================================================
+# train mode: batch-statistics BatchNorm, backward kernels, Adam (include/lpd_b200.h, "TRAIN MODE")
+# =====================================================================================================================
+SM_COUNT = 148
+
+
+def _nparts(rows: int, per: int = 64) -> int:
+    return int(max(1, min(SM_COUNT * 8, (rows + per - 1) // per)))
+
+
+def _partial(nparts: int, C: int, dev) -> torch.Tensor:
+    return torch.empty(nparts * 2 * C, device=dev, dtype=torch.float64)
+
+
+def bn_finalize(partial, nparts, count, C, gamma, beta, eps, momentum, running_mean, running_var):
+    """-> bn block [4, C] (scale, shift, mean, invstd); running stats updated in place."""
+    lib = _lib.load()
+    bn = torch.empty(4, C, device=partial.device, dtype=torch.float32)
+    _call("lpd_bn_finalize", 1, lib.lpd_bn_finalize, partial.data_ptr(), nparts, float(count), C, _p(gamma), _p(beta), float(eps),
+          float(momentum), _p(running_mean), _p(running_var), bn.data_ptr(), _stream())
+    return bn
+
+
+def bn_stats(z, rows, C, ld):
+    """column (sum, sum of squares) partials of z [rows, C] (ld) -> (partial, nparts)"""
+    lib = _lib.load()
+    nparts = _nparts(rows)
+    part = _partial(nparts, C, z.device)
+    _call(f"lpd_bn_stats[C={C}]", 1, lib.lpd_bn_stats, z.data_ptr(), rows, C, ld, part.data_ptr(), nparts, _stream())
+    return part, nparts
+
+
+def colsum_finalize(partial, nparts, n):
+    lib = _lib.load()
+    out = torch.empty(n, device=partial.device, dtype=torch.float32)
+    _call("lpd_colsum_finalize", 1, lib.lpd_colsum_finalize, partial.data_ptr(), nparts, n, out.data_ptr(), _stream())
+    return out
+
+
+def affine_act(z, rows, C, ldz, scale, shift, act=ACT_NONE, slope=0.0, aux=None, ldaux=0, out=None, ldo=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(rows, C, device=z.device, dtype=torch.float32)
+        ldo = C
+    _call(f"lpd_affine_act[C={C}]", 1, lib.lpd_affine_act, z.data_ptr(), rows, C, ldz, _p(scale), _p(shift), act, float(slope),
+          _p(aux), ldaux, out.data_ptr(), ldo, _stream())
+    return out
+
+
+def bn_bwd(dy, lddy, z, ldz, rows, C, bn, act, slope, count=None, aux=None, ldaux=0, dz=None, lddz=None):
+    """backward of act(BN_batch(z)) -> (dz [rows, C], S [2, C] = (dbeta, dgamma)); dz may alias dy."""
+    lib = _lib.load()
+    nparts = _nparts(rows)
+    part = _partial(nparts, C, z.device)
+    _call(f"lpd_bn_bwd_reduce[C={C}]", 1, lib.lpd_bn_bwd_reduce, dy.data_ptr(), lddy, z.data_ptr(), ldz, rows, C, bn.data_ptr(),
+          act, float(slope), _p(aux), ldaux, part.data_ptr(), nparts, _stream())
+    S = colsum_finalize(part, nparts, 2 * C).view(2, C)
+    if dz is None:
+        dz = torch.empty(rows, C, device=z.device, dtype=torch.float32)
+        lddz = C
+    _call(f"lpd_bn_bwd_apply[C={C}]", 1, lib.lpd_bn_bwd_apply, dy.data_ptr(), lddy, z.data_ptr(), ldz, rows, C, bn.data_ptr(),
+          S.data_ptr(), float(rows if count is None else count), act, float(slope), _p(aux), ldaux, dz.data_ptr(), lddz, _stream())
+    return dz, S
+
+
+def bn_bwd_sums(dy, lddy, z, ldz, rows, C, bn, act, slope):
+    """only the (S1, S2) sums of the BN backward (used for arg-routed edge gradients)"""
+    lib = _lib.load()
+    nparts = _nparts(rows)
+    part = _partial(nparts, C, z.device)
+    _call(f"lpd_bn_bwd_reduce[C={C}]", 1, lib.lpd_bn_bwd_reduce, dy.data_ptr(), lddy, z.data_ptr(), ldz, rows, C, bn.data_ptr(),
+          act, float(slope), None, 0, part.data_ptr(), nparts, _stream())
+    return colsum_finalize(part, nparts, 2 * C).view(2, C)
+
+
+def edge_sel_stats(p, ldp, q, ldq, idx, B, N, k, C, gamma):
+    """-> (zsel [M, C], arg uint8 [M, C], partial, nparts) for z = p_j + q_i over all edges"""
+    lib = _lib.load()
+    M = B * N
+    zsel = torch.empty(M, C, device=p.device, dtype=torch.float32)
+    arg = torch.empty(M, C, device=p.device, dtype=torch.uint8)
+    nparts = SM_COUNT * 8
+    part = _partial(nparts, C, p.device)
+    _call(f"lpd_edge_sel_stats[C={C}]", 1, lib.lpd_edge_sel_stats, p.data_ptr(), ldp, _p(q), ldq, idx.data_ptr(), B, N, k, C,
+          _p(gamma), zsel.data_ptr(), C, arg.data_ptr(), part.data_ptr(), nparts, _stream())
+    return zsel, arg, part, nparts
+
+
+def edge_materialize(p, ldp, q, ldq, idx, B, N, k, C, scale, shift, act, slope):
+    lib = _lib.load()
+    y = torch.empty(B * N * k, C, device=p.device, dtype=torch.float32)
+    _call(f"lpd_edge_materialize[C={C}]", 1, lib.lpd_edge_materialize, p.data_ptr(), ldp, _p(q), ldq, idx.data_ptr(), B, N, k, C,
+          scale.data_ptr(), shift.data_ptr(), act, float(slope), y.data_ptr(), _stream())
+    return y
+
+
+def edge_sel_dense(z, M, k, C, gamma):
+    lib = _lib.load()
+    zsel = torch.empty(M, C, device=z.device, dtype=torch.float32)
+    arg = torch.empty(M, C, device=z.device, dtype=torch.uint8)
+    _call(f"lpd_edge_sel_dense[C={C}]", 1, lib.lpd_edge_sel_dense, z.data_ptr(), M, k, C, _p(gamma), zsel.data_ptr(), C,
+          arg.data_ptr(), _stream())
+    return zsel, arg
+
+
+def edge_dense_bwd_apply(z, M, k, C, bn, S, count, act, slope, dx, lddx, zsel, arg):
+    """in place on z: -> dz [M*k, C]"""
+    lib = _lib.load()
+    _call(f"lpd_edge_dense_bwd_apply[C={C}]", 1, lib.lpd_edge_dense_bwd_apply, z.data_ptr(), M, k, C, bn.data_ptr(), S.data_ptr(),
+          float(count), act, float(slope), dx.data_ptr(), lddx, zsel.data_ptr(), C, arg.data_ptr(), z.data_ptr(), _stream())
+    return z
+
+
+def edge_bwd(p, ldp, q, ldq, idx, B, N, k, C, bn, act, slope, dx, lddx, arg, dy, dp, lddp, dq, lddq, S=None):
+    """backward of a decomposed edge layer: fills dp (atomics, zeroed first) and dq; returns S [2, C] (dbeta, dgamma).
+    If S is given (arg-routed gradient only: computed over the [M, C] arrays) the gather-reduce pass is skipped."""
+    lib = _lib.load()
+    count = B * N * k
+    if S is None:
+        nparts = SM_COUNT * 8
+        part = _partial(nparts, C, p.device)
+        _call(f"lpd_edge_bwd_reduce[C={C}]", 1, lib.lpd_edge_bwd_reduce, p.data_ptr(), ldp, _p(q), ldq, idx.data_ptr(), B, N, k, C,
+              bn.data_ptr(), act, float(slope), _p(dx), lddx, _p(arg), _p(dy), part.data_ptr(), nparts, _stream())
+        S = colsum_finalize(part, nparts, 2 * C).view(2, C)
+    _call(f"lpd_edge_bwd_apply[C={C}]", 2, lib.lpd_edge_bwd_apply, p.data_ptr(), ldp, _p(q), ldq, idx.data_ptr(), B, N, k, C,
+          bn.data_ptr(), act, float(slope), _p(dx), lddx, _p(arg), _p(dy), S.data_ptr(), float(count),
+          dp.data_ptr(), lddp, _p(dq), lddq, _stream())
+    return S
+
+
+def netvlad_finish_train(vlad, a, wc2, B, N, D, K=64):
+    """in place on vlad [B, D, K] -> (v [B, D*K], asum [B, K], n1 [B, K], n2 [B])"""
+    lib = _lib.load()
+    dev = vlad.device
+    asum = torch.empty(B, K, device=dev, dtype=torch.float32)
+    n1 = torch.empty(B, K, device=dev, dtype=torch.float32)
+    n2 = torch.empty(B, device=dev, dtype=torch.float32)
+    _call("lpd_netvlad_finish_train", 1, lib.lpd_netvlad_finish_train, vlad.data_ptr(), a.data_ptr(), wc2.data_ptr(), B, N, D, K,
+          asum.data_ptr(), n1.data_ptr(), n2.data_ptr(), _stream())
+    return vlad.view(B, D * K), asum, n1, n2
+
+
+def netvlad_finish_bwd(dv, v, wc2, asum, n1, n2, B, D, K=64):
+    """in place on dv [B, D*K] -> (dvraw [B, D, K], dasum [B, K], dwc2 [D, K])"""
+    lib = _lib.load()
+    dasum = torch.empty(B, K, device=dv.device, dtype=torch.float32)
+    dwc2 = torch.empty(D, K, device=dv.device, dtype=torch.float32)
+    _call("lpd_netvlad_finish_bwd", 2, lib.lpd_netvlad_finish_bwd, dv.data_ptr(), v.data_ptr(), wc2.data_ptr(), asum.data_ptr(),
+          n1.data_ptr(), n2.data_ptr(), B, D, K, dasum.data_ptr(), dwc2.data_ptr(), _stream())
+    return dv.view(B, D, K), dasum, dwc2
+
+
+def softmax64_bwd(da, a, dasum, M, N):
+    lib = _lib.load()
+    _call("lpd_softmax64_bwd", 1, lib.lpd_softmax64_bwd, da.data_ptr(), a.data_ptr(), _p(dasum), M, N, _stream())
+    return da
+
+
+def colmax_arg(x, B, N, C, ldx=None):
+    lib = _lib.load()
+    out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    arg = torch.empty(B, C, device=x.device, dtype=torch.int32)
+    _call("lpd_colmax_arg", 1, lib.lpd_colmax_arg, x.data_ptr(), B, N, C, C if ldx is None else ldx, out.data_ptr(), arg.data_ptr(), _stream())
+    return out, arg
+
+
+def colmax_bwd(dout, arg, B, N, C, dx, lddx):
+    lib = _lib.load()
+    _call("lpd_colmax_bwd", 1, lib.lpd_colmax_bwd, dout.data_ptr(), arg.data_ptr(), B, N, C, dx.data_ptr(), lddx, _stream())
+    return dx
+
+
+def adam(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    lib = _lib.load()
+    _call("lpd_adam", 1, lib.lpd_adam, w.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), w.numel(), float(lr), float(beta1),
+          float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _stream())
+
+
+def axpy(y, ldy, x, ldx, rows, C, alpha=1.0):
+    lib = _lib.load()
+    _call("lpd_axpy", 1, lib.lpd_axpy, y.data_ptr(), ldy, x.data_ptr(), ldx, rows, C, float(alpha), _stream())
+    return y
+
+
+def wgrad(dz, lddz, a, lda, rows, Nout, Kin, out=None):
+    """dW[n][k] = sum_r dz[r][n] * a[r][k]  (weight gradient of z = a . W^T), split over the rows and reduced in a fixed
+    order (deterministic).  -> [Nout, Kin]"""
+    tiles = ((Nout + 127) // 128) * ((Kin + 127) // 128)
+    want = max(1, min(512, (2 * SM_COUNT + tiles - 1) // tiles, rows // 256 if rows >= 256 else 1))
+    splits = 1
+    while splits * 2 <= want and rows % (splits * 2) == 0:
+        splits *= 2
+    per = rows // splits
+    part = torch.empty(splits, Nout, Kin, device=dz.device, dtype=torch.float32)
+    gemm(dz, a, a_layout=A_KM, b_layout=B_KN, M=Nout, N=Kin, K=per, lda=lddz, ldb=lda, out=part, ldc=Kin,
+         batch=splits, strideA=per * lddz, strideB=per * lda, strideC=Nout * Kin)
+    if splits == 1 and out is None:
+        return part[0]
+    res = splitk_reduce(part, splits, Nout, Kin)
+    if out is not None:
+        axpy(out, Kin, res, Kin, Nout, Kin, 1.0)
+        return out
+    return res

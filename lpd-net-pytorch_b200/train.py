@@ -1,0 +1,351 @@
+"""Train-mode execution of the hot path: forward with batch-statistics BatchNorm, hand-written backward, all through
+the C ABI (include/lpd_b200.h, "TRAIN MODE").  Replaces what torch autograd does for the reference in
+train_pointnetvlad.py:121-130,150-159 (model.train(); output = model(feed); loss.backward(); optimizer.step()).
+
+The public entry is `forward_train(model, x)`: it returns the [B, output_dim] descriptors as a tensor that is attached
+to the autograd graph through ONE torch.autograd.Function whose backward runs the kernels below and hands the
+parameter gradients back to torch (so `loss.backward()` fills `.grad` exactly as in the reference and any
+torch.optim optimizer, or lpdnet_b200.optim.Adam, can step).  torch itself does no arithmetic here: it owns the device
+memory, the current stream and the parameter / gradient storage.
+
+Layout: feature maps are point-major [rows, C]; every layer object below keeps what its backward needs.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._host import require_cuda, w2d
+from ._lib import LpdError
+
+A_MK, A_KM, B_NK, B_KN = ops.A_MK, ops.A_KM, ops.B_NK, ops.B_KN
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# layer records
+# ----------------------------------------------------------------------------------------------------------------------
+class _Grads:
+    """parameter -> gradient tensor (in the parameter's own shape); accumulates when a parameter is hit twice"""
+
+    def __init__(self):
+        self.by_param = {}
+
+    def add(self, param: torch.Tensor, g: torch.Tensor):
+        g = g.reshape(param.shape)
+        cur = self.by_param.get(param)
+        if cur is None:
+            self.by_param[param] = g.contiguous()
+        else:
+            n = cur.numel()
+            ops.axpy(cur.view(1, n), n, g.contiguous().view(1, n), n, 1, n, 1.0)
+
+
+class Linear:
+    """z = a . W^T (+ bias)     a [rows, K] (lda), W [N, K] (a conv1x1 / nn.Linear weight)"""
+
+    def fwd(self, a, lda, rows, weight: nn.Parameter, bias=None, tf32_ok=True):
+        self.a, self.lda, self.rows = a, lda, rows
+        self.weight, self.bias = weight, bias
+        self.w = w2d(weight)
+        self.N, self.K = self.w.shape
+        lin = ops.linear if tf32_ok else ops.gemm
+        return lin(a, self.w, M=rows, N=self.N, K=self.K, lda=lda, shift=None if bias is None else bias.detach())
+
+    def bwd(self, dz, lddz, grads: _Grads, need_da=True, da_out=None, ldda=None, accumulate=False):
+        grads.add(self.weight, ops.wgrad(dz, lddz, self.a, self.lda, self.rows, self.N, self.K))
+        if self.bias is not None:
+            part, nparts = ops.bn_stats(dz, self.rows, self.N, lddz) if self.N % 4 == 0 and lddz % 4 == 0 else (None, 0)
+            if part is None:
+                raise LpdError("bias gradient needs a channel count that is a multiple of 4")
+            grads.add(self.bias, ops.colsum_finalize(part, nparts, 2 * self.N)[: self.N])
+        if not need_da:
+            return None
+        if da_out is None:
+            return ops.gemm(dz, self.w, a_layout=A_MK, b_layout=B_KN, M=self.rows, N=self.K, K=self.N, lda=lddz, ldb=self.K)
+        return ops.gemm(dz, self.w, a_layout=A_MK, b_layout=B_KN, M=self.rows, N=self.K, K=self.N, lda=lddz, ldb=self.K,
+                        out=da_out, ldc=ldda, act=ops.ACT_ADD if accumulate else ops.ACT_NONE, aux=da_out if accumulate else None)
+
+
+def _bn_params(bn: nn.modules.batchnorm._BatchNorm):
+    g = bn.weight.detach() if bn.affine else None
+    b = bn.bias.detach() if bn.affine else None
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    return g, b, mom
+
+
+def _bn_finalize(bn: nn.modules.batchnorm._BatchNorm, part, nparts, count, C):
+    g, b, mom = _bn_params(bn)
+    track = bn.track_running_stats and bn.running_mean is not None
+    blk = ops.bn_finalize(part, nparts, count, C, g, b, bn.eps, mom, bn.running_mean if track else None,
+                          bn.running_var if track else None)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)       # bookkeeping counter (int64 buffer), as torch does
+    return blk
+
+
+class BNAct:
+    """y = act(BatchNorm_batch(z))   z [rows, C] (ldz); statistics over the rows"""
+
+    def fwd(self, z, ldz, rows, C, bn: nn.modules.batchnorm._BatchNorm, act=ops.ACT_NONE, slope=0.0, aux=None, ldaux=0,
+            out=None, ldo=None):
+        self.z, self.ldz, self.rows, self.C, self.bn_mod = z, ldz, rows, C, bn
+        self.act, self.slope, self.aux, self.ldaux = act, slope, aux, ldaux
+        part, nparts = ops.bn_stats(z, rows, C, ldz)
+        self.bn = _bn_finalize(bn, part, nparts, rows, C)
+        return ops.affine_act(z, rows, C, ldz, self.bn[0], self.bn[1], act, slope, aux, ldaux, out, ldo)
+
+    def bwd(self, dy, lddy, grads: _Grads, inplace=True):
+        dz, S = ops.bn_bwd(dy, lddy, self.z, self.ldz, self.rows, self.C, self.bn, self.act, self.slope, aux=self.aux,
+                           ldaux=self.ldaux, dz=dy if inplace else None, lddz=lddy if inplace else None)
+        if self.bn_mod.affine:
+            grads.add(self.bn_mod.bias, S[0])
+            grads.add(self.bn_mod.weight, S[1])
+        return dz
+
+
+def _act_of(module):
+    return (ops.ACT_RELU, 0.0) if isinstance(module.act_f, nn.ReLU) else (ops.ACT_LEAKY, module.negative_slope)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# LPDNet (reference lpdnet_model.py:147-268), train mode
+# ----------------------------------------------------------------------------------------------------------------------
+class LPDNetTrain:
+    def __init__(self, net):
+        if net.t3d or net.tfea:
+            raise LpdError("train mode with T-Nets (xyz_trans / feature_transform) is not built yet")
+        if net.use_mFea:
+            raise LpdError("train mode with use_mFea is not built yet")
+        self.net = net
+
+    def fwd(self, x):
+        net = self.net
+        require_cuda(x, "LPDNet")
+        B, _, N, D = x.shape
+        M, k = B * N, net.k
+        self.B, self.N, self.M, self.k = B, N, M, k
+        act, slope = _act_of(net)
+        self.act, self.slope = act, slope
+        dev = x.device
+        rows = x.detach().reshape(M, D).contiguous()
+        xyz = rows.view(B, N, 3)
+        # conv1 / conv2 (+BN+act): always strict fp32 — they feed the feature-space kNN (see _LPDBase._front)
+        self.l1, self.b1, self.l2, self.b2 = Linear(), BNAct(), Linear(), BNAct()
+        z1 = self.l1.fwd(rows, D, M, net.conv1_lpd.weight, tf32_ok=False)
+        h1 = self.b1.fwd(z1, 64, M, 64, net.bn1_lpd, act, slope)
+        z2 = self.l2.fwd(h1, 64, M, net.conv2_lpd.weight, tf32_ok=False)
+        h2 = self.b2.fwd(z2, 64, M, 64, net.bn2_lpd, act, slope)
+        self.h2 = h2
+        # ---- feature-space graph: DG1 (decomposed) -> x1, DG2 (dense edge GEMM) -> x2 --------------------------------
+        self.idx_f = ops.knn(h2.view(B, N, 64), k)
+        wdg1 = w2d(net.convDG1[0].weight)                                         # [128, 128] = [Wn | Wc]
+        self.wpq1 = torch.cat((wdg1[:, :64], wdg1[:, 64:]), 0).contiguous()       # [256, 64]
+        self.pq1 = ops.linear(h2, self.wpq1, M=M, N=256, K=64)
+        p1, q1 = self.pq1, self.pq1[:, 128:]
+        bn_dg1, bn_dg2, bn_sn1 = net.convDG1[1], net.convDG2[1], net.convSN1[1]
+        self.zsel1, self.arg1, part, nparts = ops.edge_sel_stats(p1, 256, q1, 256, self.idx_f, B, N, k, 128, bn_dg1.weight.detach())
+        self.bn1e = _bn_finalize(bn_dg1, part, nparts, M * k, 128)
+        self.pyr = torch.empty(M, 512, device=dev, dtype=torch.float32)
+        pyr = self.pyr
+        ops.affine_act(self.zsel1, M, 128, 128, self.bn1e[0], self.bn1e[1], act, slope, out=pyr, ldo=512)
+        self.y1 = ops.edge_materialize(p1, 256, q1, 256, self.idx_f, B, N, k, 128, self.bn1e[0], self.bn1e[1], act, slope)
+        self.wdg2 = w2d(net.convDG2[0].weight)
+        self.z2e = ops.linear(self.y1, self.wdg2, M=M * k, N=128, K=128)
+        part, nparts = ops.bn_stats(self.z2e, M * k, 128, 128)
+        self.bn2e = _bn_finalize(bn_dg2, part, nparts, M * k, 128)
+        self.zsel2, self.arg2 = ops.edge_sel_dense(self.z2e, M, k, 128, bn_dg2.weight.detach())
+        ops.affine_act(self.zsel2, M, 128, 128, self.bn2e[0], self.bn2e[1], act, slope, out=pyr[:, 128:], ldo=512)
+        # ---- Cartesian graph on the input coordinates: SN1 (decomposed) over x2 -> x3 ---------------------------------
+        self.idx_x = ops.knn(xyz, k)
+        wsn1 = w2d(net.convSN1[0].weight)                                         # [256, 256]
+        self.wpq3 = torch.cat((wsn1[:, :128], wsn1[:, 128:]), 0).contiguous()     # [512, 128]
+        self.pq3 = ops.linear(pyr[:, 128:], self.wpq3, M=M, N=512, K=128, lda=512)
+        p3, q3 = self.pq3, self.pq3[:, 256:]
+        self.zsel3, self.arg3, part, nparts = ops.edge_sel_stats(p3, 512, q3, 512, self.idx_x, B, N, k, 256, bn_sn1.weight.detach())
+        self.bn3e = _bn_finalize(bn_sn1, part, nparts, M * k, 256)
+        ops.affine_act(self.zsel3, M, 256, 256, self.bn3e[0], self.bn3e[1], act, slope, out=pyr[:, 256:], ldo=512)
+        # ---- conv3 512 -> emb ---------------------------------------------------------------------------------------------
+        self.l3, self.b3 = Linear(), BNAct()
+        z3 = self.l3.fwd(pyr, 512, M, net.conv3_lpd.weight)
+        f = self.b3.fwd(z3, net.emb_dims, M, net.emb_dims, net.bn3_lpd, act, slope)
+        return f, B, N
+
+    def bwd(self, df, grads: _Grads):
+        """df [M, emb] (consumed in place)"""
+        net, B, N, M, k = self.net, self.B, self.N, self.M, self.k
+        act, slope = self.act, self.slope
+        dev = df.device
+        dz3 = self.b3.bwd(df, net.emb_dims, grads)
+        dpyr = self.l3.bwd(dz3, net.emb_dims, grads)                               # [M, 512]
+        del dz3, df
+        # ---- SN1: arg-routed gradient only -------------------------------------------------------------------------------
+        bn_dg1, bn_dg2, bn_sn1 = net.convDG1[1], net.convDG2[1], net.convSN1[1]
+        dx3 = dpyr[:, 256:]
+        S3 = ops.bn_bwd_sums(dx3, 512, self.zsel3, 256, M, 256, self.bn3e, act, slope)
+        dpq3 = torch.empty(M, 512, device=dev, dtype=torch.float32)
+        ops.edge_bwd(self.pq3, 512, self.pq3[:, 256:], 512, self.idx_x, B, N, k, 256, self.bn3e, act, slope, dx3, 512, self.arg3,
+                     None, dpq3, 512, dpq3[:, 256:], 512, S=S3)
+        grads.add(bn_sn1.bias, S3[0])
+        grads.add(bn_sn1.weight, S3[1])
+        dwpq3 = ops.wgrad(dpq3, 512, self.pyr[:, 128:], 512, M, 512, 128)          # [512, 128]
+        grads.add(net.convSN1[0].weight, torch.cat((dwpq3[:256], dwpq3[256:]), 1))
+        dx2 = dpyr[:, 128:]
+        ops.gemm(dpq3, self.wpq3, a_layout=A_MK, b_layout=B_KN, M=M, N=128, K=512, lda=512, ldb=128, out=dx2, ldc=512,
+                 act=ops.ACT_ADD, aux=dx2)
+        del dpq3
+        # ---- DG2: dense edge layer whose only consumer is the max ----------------------------------------------------
+        S2 = ops.bn_bwd_sums(dx2, 512, self.zsel2, 128, M, 128, self.bn2e, act, slope)
+        dz2e = ops.edge_dense_bwd_apply(self.z2e, M, k, 128, self.bn2e, S2, M * k, act, slope, dx2, 512, self.zsel2, self.arg2)
+        grads.add(bn_dg2.bias, S2[0])
+        grads.add(bn_dg2.weight, S2[1])
+        grads.add(net.convDG2[0].weight, ops.wgrad(dz2e, 128, self.y1, 128, M * k, 128, 128))
+        dy1 = ops.gemm(dz2e, self.wdg2, a_layout=A_MK, b_layout=B_KN, M=M * k, N=128, K=128, lda=128, ldb=128,
+                       out=self.y1, ldc=128)                                       # y1 is dead after the wgrad: reuse it
+        # ---- DG1: dense gradient from DG2 + arg-routed gradient of x1 -----------------------------------------------
+        dpq1 = torch.empty(M, 256, device=dev, dtype=torch.float32)
+        S1 = ops.edge_bwd(self.pq1, 256, self.pq1[:, 128:], 256, self.idx_f, B, N, k, 128, self.bn1e, act, slope, dpyr, 512,
+                          self.arg1, dy1, dpq1, 256, dpq1[:, 128:], 256)
+        grads.add(bn_dg1.bias, S1[0])
+        grads.add(bn_dg1.weight, S1[1])
+        dwpq1 = ops.wgrad(dpq1, 256, self.h2, 64, M, 256, 64)                      # [256, 64]
+        grads.add(net.convDG1[0].weight, torch.cat((dwpq1[:128], dwpq1[128:]), 1))
+        dh2 = ops.gemm(dpq1, self.wpq1, a_layout=A_MK, b_layout=B_KN, M=M, N=64, K=256, lda=256, ldb=64)
+        del dpq1, dy1, dpyr
+        dz2 = self.b2.bwd(dh2, 64, grads)
+        dh1 = self.l2.bwd(dz2, 64, grads)
+        dz1 = self.b1.bwd(dh1, 64, grads)
+        self.l1.bwd(dz1, 64, grads, need_da=False)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# NetVLADLoupe + GatingContext (reference PointNetVlad.py:12-115), train mode
+# ----------------------------------------------------------------------------------------------------------------------
+class NetVLADTrain:
+    def __init__(self, nv):
+        if nv.cluster_size != 64:
+            raise NotImplementedError("the NetVLAD kernels are specialised for cluster_size == 64 (the reference's value)")
+        if not nv.add_batch_norm:
+            raise LpdError("train mode without add_batch_norm is not built yet")
+        self.nv = nv
+
+    def fwd(self, f, B):
+        nv = self.nv
+        N, D, K, O = nv.max_samples, nv.feature_size, nv.cluster_size, nv.output_dim
+        M = B * N
+        self.f, self.B, self.M = f, B, M
+        wc = nv.cluster_weights.detach()
+        # soft assignment: a = softmax(BN(f . Wc))                                            :48-59
+        self.apre = ops.gemm(f, wc, a_layout=A_MK, b_layout=B_KN, M=M, N=K, K=D, lda=D, ldb=K)
+        self.bn_a = BNAct()
+        a = self.bn_a.fwd(self.apre, K, M, K, nv.bn1)
+        self.a = ops.softmax64(a, M)
+        vraw = ops.gemm(f, self.a, a_layout=A_KM, b_layout=B_KN, M=D, N=K, K=N, lda=D, ldb=K, batch=B,
+                        strideA=N * D, strideB=N * K)                                         # :64-66 -> [B, D, K]
+        vraw = vraw.view(B, D, K)
+        self.v, self.asum, self.n1, self.n2 = ops.netvlad_finish_train(vraw, self.a, nv.cluster_weights2.detach()[0].contiguous(),
+                                                                       B, N, D, K)            # :61-74
+        KD = D * K
+        splits = nv.HIDDEN_SPLITS
+        while KD % splits:
+            splits //= 2
+        kc = KD // splits
+        wh = nv.hidden1_weights.detach()
+        part = torch.empty(splits, B, O, device=f.device, dtype=torch.float32)
+        ops.gemm(self.v, wh, a_layout=A_MK, b_layout=B_KN, M=B, N=O, K=kc, lda=KD, ldb=O, out=part, ldc=O,
+                 batch=splits, strideA=kc, strideB=kc * O, strideC=B * O)                     # :76
+        hpre = ops.splitk_reduce(part, splits, B, O)
+        self.bn_h = BNAct()
+        h = self.bn_h.fwd(hpre, O, B, O, nv.bn2)                                              # :78
+        self.h = h
+        if not nv.gating:
+            return h
+        cg = nv.context_gating
+        self.g = ops.gemm(h, cg.gating_weights.detach(), a_layout=A_MK, b_layout=B_KN, M=B, N=O, K=O)   # :104
+        self.bn_g = BNAct()
+        return self.bn_g.fwd(self.g, O, B, O, cg.bn1, ops.ACT_GATE, 0.0, aux=h, ldaux=O)        # :106-113
+
+    def bwd(self, dout, grads: _Grads):
+        """dout [B, O] -> df [M, D]"""
+        nv = self.nv
+        N, D, K, O = nv.max_samples, nv.feature_size, nv.cluster_size, nv.output_dim
+        B, M = self.B, self.M
+        dout = dout.contiguous()
+        if nv.gating:
+            cg = nv.context_gating
+            wg = cg.gating_weights.detach()
+            # out = h * sigmoid(BN(g)):  dh (direct) = dout * sigmoid(.) ; dg through the BN
+            dh = ops.affine_act(self.g, B, O, O, self.bn_g.bn[0], self.bn_g.bn[1], ops.ACT_GATE, 0.0, aux=dout, ldaux=O)
+            dg = self.bn_g.bwd(dout, O, grads, inplace=False)
+            grads.add(cg.gating_weights, ops.gemm(self.h, dg, a_layout=A_KM, b_layout=B_KN, M=O, N=O, K=B, lda=O, ldb=O))
+            ops.gemm(dg, wg, a_layout=A_MK, b_layout=B_NK, M=B, N=O, K=O, lda=O, ldb=O, out=dh, ldc=O, act=ops.ACT_ADD, aux=dh)
+        else:
+            dh = dout.clone()
+        dhpre = self.bn_h.bwd(dh, O, grads)
+        wh = nv.hidden1_weights.detach()
+        KD = D * K
+        grads.add(nv.hidden1_weights, ops.gemm(self.v, dhpre, a_layout=A_KM, b_layout=B_KN, M=KD, N=O, K=B, lda=KD, ldb=O))
+        dv = ops.gemm(dhpre, wh, a_layout=A_MK, b_layout=B_NK, M=B, N=KD, K=O, lda=O, ldb=O)   # [B, D*K]
+        wc2 = nv.cluster_weights2.detach()[0].contiguous()
+        dvraw, dasum, dwc2 = ops.netvlad_finish_bwd(dv, self.v, wc2, self.asum, self.n1, self.n2, B, D, K)
+        grads.add(nv.cluster_weights2, dwc2)
+        f, a = self.f, self.a
+        # vraw[b] = f[b]^T a[b]:  df[b] = a[b] . dvraw[b]^T ;  da[b] = f[b] . dvraw[b]
+        df = ops.gemm(a, dvraw, a_layout=A_MK, b_layout=B_NK, M=N, N=D, K=K, lda=K, ldb=K, batch=B,
+                      strideA=N * K, strideB=D * K, strideC=N * D,
+                      out=torch.empty(M, D, device=f.device, dtype=torch.float32), ldc=D)
+        da = ops.gemm(f, dvraw, a_layout=A_MK, b_layout=B_KN, M=N, N=K, K=D, lda=D, ldb=K, batch=B,
+                      strideA=N * D, strideB=D * K, strideC=N * K,
+                      out=torch.empty(M, K, device=f.device, dtype=torch.float32), ldc=K)
+        ds = ops.softmax64_bwd(da, a, dasum, M, N)
+        dapre = self.bn_a.bwd(ds, K, grads)
+        wc = nv.cluster_weights.detach()
+        grads.add(nv.cluster_weights, ops.wgrad(f, D, dapre, K, M, D, K))           # dWc[d][k] = sum_m f[m][d] dapre[m][k]
+        ops.gemm(dapre, wc, a_layout=A_MK, b_layout=B_NK, M=M, N=D, K=K, lda=K, ldb=K, out=df, ldc=D, act=ops.ACT_ADD, aux=df)
+        return df
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# whole model
+# ----------------------------------------------------------------------------------------------------------------------
+class _PointNetVladTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, model, *params):
+        feat = model.emb_nn
+        from .util.lpdnet_model import LPDNet
+        if not isinstance(feat, LPDNet):
+            raise LpdError("train mode is built for featnet='lpdnet' (the C3 configuration) in this round; "
+                           "featnet='pointnet' / 'lpdnetorigin' train() is not built yet — use .eval()")
+        with torch.no_grad():
+            fe = LPDNetTrain(feat)
+            f, B, N = fe.fwd(x)
+            if N != model.net_vlad.max_samples:
+                raise ValueError(f"PointNetVlad: got {N} points per cloud, constructed for num_points={model.net_vlad.max_samples}")
+            nv = NetVLADTrain(model.net_vlad)
+            out = nv.fwd(f, B)
+        ctx.fe, ctx.nv, ctx.params = fe, nv, params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = _Grads()
+        with torch.no_grad():
+            df = ctx.nv.bwd(dout, grads)
+            ctx.fe.bwd(df, grads)
+        out = [grads.by_param.get(p) for p in ctx.params]
+        ctx.fe = ctx.nv = None
+        return (None, None, *out)
+
+
+def forward_train(model, x: torch.Tensor) -> torch.Tensor:
+    """train-mode PointNetVlad.forward (reference PointNetVlad.py:261-270 under model.train())"""
+    require_cuda(x, "PointNetVlad")
+    params = [p for p in model.parameters() if p.requires_grad]
+    if not torch.is_grad_enabled() or not params:
+        with torch.no_grad():
+            return _PointNetVladTrainFn.forward(_NullCtx(), x, model, *params)
+    return _PointNetVladTrainFn.apply(x, model, *params)
+
+
+class _NullCtx:
+    pass

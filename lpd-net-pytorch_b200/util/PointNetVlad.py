@@ -305,6 +305,10 @@ class PointNetVlad(nn.Module):
                                      output_dim=output_dim, gating=True, add_batch_norm=True, is_training=True)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            # batch-statistics BatchNorm + hand-written backward behind one autograd node (lpdnet_b200/train.py)
+            from ..train import forward_train
+            return forward_train(self, x)
         if self.emb_nn is not None:
             f, B, N = self.emb_nn.forward_pm(x)
         else:

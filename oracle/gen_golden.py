@@ -185,7 +185,50 @@ def case_recall(L, PNV, RL):
          db0_sha=sha(DB[0]), q0_sha=sha(Q[0]))
 
 
-CASES = {"knn": case_knn, "c1": case_c1_pointnet, "c2": case_c2_lpdnet, "loss": case_loss, "recall": case_recall}
+def subsample(t, n=4096):
+    """fixed subsample of a (gradient) tensor: every s-th element of the flattened tensor, at most n values"""
+    flat = t.detach().reshape(-1)
+    s_ = max(1, flat.numel() // n)
+    return flat[::s_][:n].numpy().copy()
+
+
+def case_c3_train_step(L, PNV, RL):
+    """C3: one LPD-Net training step of the reference (train-mode forward, lazy quadruplet loss, autograd backward) on
+    one tuple = 1 query + 2 positives + 18 negatives + 1 other negative = 22 clouds (run_model order,
+    train_pointnetvlad.py:202-217), at a reduced point count so the fixture stays small."""
+    for name, N, Bq in (("c3_train_step_n256", 256, 1), ("c3_train_step_n512_b2", 512, 2)):
+        arrays = {}
+        # fp32 = the reference as shipped; fp64 = the same code in double, the yardstick for the fp32 run's own rounding
+        # noise (LeakyReLU sign / arg-max / near-tie kNN flips move isolated gradient entries by up to ~1e-2 of the
+        # tensor's max between fp32 and fp64 runs of the reference itself)
+        for tag, dtype in (("", torch.float32), ("64", torch.float64)):
+            torch.manual_seed(1234)
+            model = PNV.PointNetVlad(num_points=N, featnet="lpdnet", emb_dims=1024)
+            sd = synth.synthetic_state_dict(model)
+            model.load_state_dict(sd)
+            model.train()
+            model = model.to(dtype)
+            P, Nn = 2, 18
+            x = synth.clouds(Bq * (1 + P + Nn + 1), N)
+            out = model(x.to(dtype))
+            o = out.view(Bq, -1, 256)
+            q, pos, neg, other = torch.split(o, [1, P, Nn, 1], dim=1)
+            loss = RL.quadruplet_loss(q, pos, neg, other, 0.5, 0.2, use_min=True, lazy=True, ignore_zero_loss=False)
+            loss.backward()
+            arrays.update({"out" + tag: out.detach().numpy(), "loss" + tag: loss.detach().numpy()})
+            for key, p_ in model.named_parameters():
+                arrays[f"grad{tag}." + key] = subsample(p_.grad).astype(np.float32)
+                arrays[f"gnorm{tag}." + key] = np.float64(p_.grad.double().norm().item())
+            if tag == "":
+                arrays.update({"x_sha": sha(x), "sd_sha": sd_digest(sd)})
+                after = model.state_dict()
+                for key in after:
+                    if key.endswith("running_mean") or key.endswith("running_var"):
+                        arrays["after." + key] = after[key].numpy()
+            print(f"  {name}{tag}: loss {float(loss.detach()):.6f}")
+        save(name, **arrays)
+
+CASES = {"knn": case_knn, "c1": case_c1_pointnet, "c2": case_c2_lpdnet, "loss": case_loss, "recall": case_recall, "c3train": case_c3_train_step}
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())

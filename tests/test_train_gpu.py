@@ -1,0 +1,114 @@
+"""C3 parity on the B200: one LPD-Net training step (train-mode forward with batch-statistics BatchNorm, lazy quadruplet
+loss, backward, Adam) through the C ABI against golden vectors produced by the UNMODIFIED reference with torch autograd
+on the CPU (oracle/gen_golden.py case_c3_train_step).
+
+Tolerances: descriptors <= 1e-4 max-abs; loss <= 1e-5 relative (BASELINE.json north_star) or 1.5x the reference's own
+fp32-vs-fp64 loss difference, whichever is larger; every parameter gradient (committed subsample, relative to the
+tensor's max-abs) within max(5e-4, 2x noise) of the reference's fp64 gradients and max(5e-4, 3x noise) of its fp32
+gradients, where noise = the reference's own fp32-vs-fp64 deviation for that tensor; L2 norms within max(5e-4, 3x noise).
+"""
+import numpy as np
+import pytest
+import torch
+
+from lpdnet_b200 import ops, optim, synth
+from lpdnet_b200.loss import pointnetvlad_loss as L
+from lpdnet_b200.util import PointNetVlad as PNV
+
+pytestmark = pytest.mark.gpu
+
+
+def subsample(t, n=4096):
+    flat = t.detach().reshape(-1)
+    s = max(1, flat.numel() // n)
+    return flat[::s][:n].cpu().numpy()
+
+
+def build_train(N):
+    model = PNV.PointNetVlad(num_points=N, featnet="lpdnet", emb_dims=1024)
+    model.load_state_dict(synth.synthetic_state_dict(model))
+    return model.cuda().train()
+
+
+def run_step(model, x, Bq, P=2, Nn=18):
+    out = model(x.cuda())
+    o = out.view(Bq, -1, 256)
+    q, pos, neg, other = torch.split(o, [1, P, Nn, 1], dim=1)
+    loss = L.quadruplet_loss(q, pos, neg, other, 0.5, 0.2, use_min=True, lazy=True, ignore_zero_loss=False)
+    loss.backward()
+    return out, loss
+
+
+@pytest.mark.parametrize("name,N,Bq", [("c3_train_step_n256", 256, 1), ("c3_train_step_n512_b2", 512, 2)])
+def test_training_step_matches_reference_autograd(cuda, golden, name, N, Bq):
+    g = golden(name)
+    ops.set_precision("fp32")
+    model = build_train(N)
+    x = synth.clouds(Bq * 22, N)
+    out, loss = run_step(model, x, Bq)
+    out = out.detach().cpu().numpy()
+    assert np.abs(out - g["out"]).max() <= 1e-4, f"train-mode descriptors: {np.abs(out - g['out']).max():.3e}"
+    # The yardstick for fp32 rounding noise is the reference itself: its fp32 run (the golden) against the same code in
+    # fp64 (golden "64" entries).  LeakyReLU-sign / arg-max / near-tie kNN flips move isolated gradient entries by up to
+    # ~1e-2 of the tensor's max between those two runs, and the loss by up to 3e-5 relative.
+    ref_loss, ref_loss64 = float(g["loss"]), float(g["loss64"])
+    loss_tol = max(1e-5 * abs(ref_loss), 1.5 * abs(ref_loss - ref_loss64))
+    assert abs(float(loss.detach()) - ref_loss) <= loss_tol, f"loss {float(loss.detach())} vs {ref_loss} (fp64 {ref_loss64})"
+    bad = {}
+    for key, p in model.named_parameters():
+        assert p.grad is not None, f"no gradient for {key}"
+        ref, ref64 = g["grad." + key], g["grad64." + key]
+        got = subsample(p.grad)
+        scale = max(np.abs(ref64).max(), 1e-12)
+        noise = np.abs(ref - ref64).max() / scale                 # the reference's own fp32-vs-fp64 deviation
+        e32 = np.abs(got - ref).max() / scale
+        e64 = np.abs(got - ref64).max() / scale
+        gn, rn = float(p.grad.double().norm()), float(g["gnorm64." + key])
+        nnoise = abs(float(g["gnorm." + key]) - rn) / max(rn, 1e-12)
+        if e64 > max(5e-4, 2.0 * noise) or e32 > max(5e-4, 3.0 * noise) or abs(gn - rn) > max(5e-4, 3.0 * nnoise) * rn:
+            bad[key] = (float(e32), float(e64), float(noise), abs(gn - rn) / rn, nnoise)
+    assert not bad, f"gradient mismatch {{key: (err vs fp32 ref, err vs fp64 ref, ref fp32-vs-fp64, norm err, ref norm noise)}}: {bad}"
+    # running statistics after the step (momentum 0.1, unbiased variance)
+    sd = model.state_dict()
+    for key in g.files:
+        if key.startswith("after."):
+            got = sd[key[6:]].cpu().numpy()
+            assert np.allclose(got, g[key], rtol=1e-4, atol=1e-5), f"{key[6:]} after one train step"
+
+
+def test_adam_matches_torch_semantics(cuda):
+    """lpd_adam against a numpy restatement of torch.optim.Adam (defaults, train_pointnetvlad.py:57)"""
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal(10007).astype(np.float32)
+    gs = [rng.standard_normal(10007).astype(np.float32) * s for s in (1.0, 0.1, 3.0)]
+    m = np.zeros_like(w, dtype=np.float64)
+    v = np.zeros_like(w, dtype=np.float64)
+    wr = w.astype(np.float64)
+    p = torch.nn.Parameter(torch.from_numpy(w.copy()).cuda())
+    opt = optim.Adam([p], lr=1e-3)
+    for t, gnp in enumerate(gs, 1):
+        m = 0.9 * m + 0.1 * gnp
+        v = 0.999 * v + 0.001 * gnp.astype(np.float64) ** 2
+        wr = wr - (1e-3 / (1 - 0.9 ** t)) * m / (np.sqrt(v) / np.sqrt(1 - 0.999 ** t) + 1e-8)
+        p.grad = torch.from_numpy(gnp).cuda()
+        opt.step()
+    assert np.abs(p.detach().cpu().numpy() - wr).max() <= 2e-6
+
+
+def test_train_then_eval_roundtrip_and_loss_decreases(cuda):
+    """a few Adam steps on one tuple: finite, the loss goes down, eval() afterwards uses the updated running statistics"""
+    ops.set_precision("fp32")
+    model = build_train(256)
+    opt = optim.Adam(model.parameters(), lr=1e-3)
+    x = synth.clouds(22, 256)
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        _, loss = run_step(model, x, 1)
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    model.eval()
+    with torch.no_grad():
+        out = model(x.cuda())
+    assert torch.isfinite(out).all()
