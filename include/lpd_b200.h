@@ -126,6 +126,14 @@ int lpd_gemm_tf32(const float* A, int lda, const float* B, int ldb, float* C, in
                   int M, int N, int K, const float* scale, const float* shift, int act, float slope,
                   void* stream);
 
+/* Tensor-core GEMM contracting over the ROWS of two point-major maps (both operands "MN-major" for the tensor core):
+ *     C[z][m][n] = sum_{k < K} A[z*K + k][m] * B[z*K + k][n]        A [batch*K][lda], B [batch*K][ldb]
+ * TF32 operands, fp32 accumulation.  Used for the NetVLAD aggregate vraw[b] = F[b]^T a[b] (PointNetVlad.py:64-66), the
+ * weight gradients dW = dZ^T A of every conv / linear layer (split over row slices z, reduced by lpd_splitk_reduce).
+ * batch > 1 requires K % 32 == 0.  Requires sm_100, 16-byte aligned bases, leading dimensions multiples of 4. */
+int lpd_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long strideC,
+                     int M, int N, int K, int batch, void* stream);
+
 /* column max over rows of each cloud: out[b][c] = max_n x[b][n][c]
  * (MaxPool2d((num_points,1)) PointNetVlad.py:137,169 ; torch.max(x,2) lpdnet_model.py:300) */
 int lpd_colmax(const float* x, int B, int N, int C, int ldx, float* out, void* stream);

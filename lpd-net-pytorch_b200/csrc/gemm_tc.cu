@@ -30,9 +30,16 @@ struct Params {
     const float* scale; const float* shift;
     float neg_slope;   // act(v) = max(v, v * neg_slope): 1 -> identity, 0 -> ReLU, 0 < s < 1 -> LeakyReLU(s)
     int tiles_m, tiles_n;
+    int batch; long long strideC;   // TN only: slice z contracts rows [z*K, (z+1)*K) of both operands into C + z*strideC
 };
 
-template <int BN, int STAGES>
+// TN == false:  C[m][n] = sum_k A[m][k] B[n][k]      (both operands K-contiguous: "K-major" UMMA tiles)
+// TN == true :  C[z][m][n] = sum_k A[z*K + k][m] B[z*K + k][n]   (both operands stored [k][m|n], i.e. "MN-major":
+//               the weight-gradient / NetVLAD-aggregate contraction over the rows of two point-major maps).  An MN-major
+//               operand tile (128B swizzle, 32-byte atom — the only MN-major layout kind::tf32 accepts) is a row of TMA boxes
+//               {32 floats, 32 k-rows}: 4-row atoms 512 B apart (SBO), 32-element MN groups one box = 4096 B apart (LBO);
+//               a K=8 MMA step advances the start address by two atoms (1024 B).
+template <int BN, int STAGES, bool TN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -48,7 +55,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + BK - 1) / BK;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int tiles_mn = p.tiles_m * p.tiles_n;
+    const int num_tiles = tiles_mn * (TN ? p.batch : 1);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -70,20 +78,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
+                const int z = t / tiles_mn, tt = t % tiles_mn;
+                const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
-                    tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m0);
-                    tma_load_2d(sa + A_BYTES, &tmap_b, &full[stage], kb * BK, n0);
+                    if (TN) {
+                        const int k0 = z * p.K + kb * BK;
+#pragma unroll
+                        for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * 4096, &tmap_a, &full[stage], m0 + i * 32, k0);
+#pragma unroll
+                        for (int i = 0; i < BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * 4096, &tmap_b, &full[stage], n0 + i * 32, k0);
+                    } else {
+                        tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m0);
+                        tma_load_2d(sa + A_BYTES, &tmap_b, &full[stage], kb * BK, n0);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
+            constexpr uint32_t idesc = make_idesc(BM, BN) | (TN ? ((1u << 15) | (1u << 16)) : 0u);   // a_major / b_major = MN
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -94,11 +111,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+                    if (TN) {
+                        const uint64_t da = make_smem_desc_mn(sa), db = make_smem_desc_mn(sa + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        tc_mma_tf32(tmem_d, da + (uint64_t)(k * UMMA_K * 4 >> 4), db + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
-                                    (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k)      // 8 k-rows (1024 B) per K=8 step
+                            tc_mma_tf32(tmem_d, da + (uint64_t)(k * 1024 >> 4), db + (uint64_t)(k * 1024 >> 4), idesc,
+                                        (kb | k) != 0 ? 1u : 0u);
+                    } else {
+                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            tc_mma_tf32(tmem_d, da + (uint64_t)(k * UMMA_K * 4 >> 4), db + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
+                                        (kb | k) != 0 ? 1u : 0u);
+                    }
                     tc_commit(&empty[stage]);           // slot reusable once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -114,7 +139,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ch = lane & 7, rsub = lane >> 3;       // read-back role: 16-byte chunk within the row, row sub-index
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
+            const int z = t / tiles_mn, tt = t % tiles_mn;
+            const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * BN;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const int row0 = m0 + q * 32;
@@ -137,7 +163,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
                     if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
                 }
-                float* gcol = p.C + (size_t)row0 * p.ldc + col;
+                float* gcol = p.C + (TN ? (size_t)z * p.strideC : (size_t)0) + (size_t)row0 * p.ldc + col;
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int rr = it * 4 + rsub;
@@ -163,18 +189,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TN = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + EPI_WARPS * 32 * 32 * 4 + 256;
-    LPD_CUDA_CHECK(allow_smem(gemm_tf32_kernel<BN, STAGES>, smem));
+    LPD_CUDA_CHECK(allow_smem(gemm_tf32_kernel<BN, STAGES, TN>, smem));
     int dev = 0, sms = 0;
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     p.tiles_m = ceil_div(p.M, BM);
     p.tiles_n = ceil_div(p.N, BN);
-    const long long tiles = (long long)p.tiles_m * p.tiles_n;
+    const long long tiles = (long long)p.tiles_m * p.tiles_n * (TN ? p.batch : 1);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_tf32_kernel<BN, STAGES><<<grid, THREADS, smem, st>>>(ta, tb, p);
+    gemm_tf32_kernel<BN, STAGES, TN><<<grid, THREADS, smem, st>>>(ta, tb, p);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }
@@ -205,9 +231,38 @@ extern "C" int lpd_gemm_tf32(const float* A, int lda, const float* B, int ldb, f
     tc::Params p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = scale; p.shift = shift;
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
-    p.tiles_m = p.tiles_n = 0;
+    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0;
     cudaStream_t st = as_stream(stream);
     if (BN == 64) return tc::launch<64, 8>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6>(ta, tb, p, st);
     return tc::launch<256, 4>(ta, tb, p, st);
+}
+
+extern "C" int lpd_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long strideC,
+                                int M, int N, int K, int batch, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1 && batch >= 1);
+    LPD_REQUIRE(lda >= M && ldb >= N && ldc >= N);
+    LPD_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0 && (strideC % 4) == 0);
+    LPD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0);
+    LPD_REQUIRE((N % 4) == 0);
+    LPD_REQUIRE(batch == 1 || (K % tc::BK) == 0);          // a slice's k-blocks must not run into the next slice
+    int dev = 0, major = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return LPD_EUNSUPPORTED;
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    const long long rows = (long long)K * batch;
+    CUtensorMap ta, tb;
+    int rc = tc::make_tmap(&ta, A, rows, M, lda, 32, true); // boxes {32 floats along M, 32 k-rows}, 32-byte swizzle atom
+    if (rc != LPD_OK) return rc;
+    rc = tc::make_tmap(&tb, B, rows, N, ldb, 32, true);
+    if (rc != LPD_OK) return rc;
+    tc::Params p;
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = nullptr; p.shift = nullptr; p.neg_slope = 1.f;
+    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = strideC;
+    cudaStream_t st = as_stream(stream);
+    if (BN == 64) return tc::launch<64, 8, true>(ta, tb, p, st);
+    if (BN == 128) return tc::launch<128, 6, true>(ta, tb, p, st);
+    return tc::launch<256, 4, true>(ta, tb, p, st);
 }

@@ -94,6 +94,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major operand tile of 32-bit elements built from TMA boxes {32 fp32 along M/N, k rows}.  For tf32 the only MN-major
+// layout the tensor core accepts is "128B swizzle with a 32-byte atom" (layout type 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+// rows of 128 B, 4-row atoms 512 B apart (stride byte offset), 32-element M/N groups one 32-row box = 4096 B apart
+// (leading byte offset).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;                  // leading byte offset: next 32 elements along M/N
+    d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: next 4 k-rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                            // SWIZZLE_128B_BASE32B
+    return d;
+}
+
 // kind::tf32, fp32 accumulate, A and B K-major
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {  // kind::tf32
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -117,7 +131,7 @@ inline EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor [rows][cols] with leading dimension ld (elements), box = [box_rows][32 cols], 128B swizzle
-inline int make_tmap(CUtensorMap* m, const float* base, long long rows, int cols, int ld, int box_rows) {
+inline int make_tmap(CUtensorMap* m, const float* base, long long rows, int cols, int ld, int box_rows, bool atom32 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled entry point not found"); return LPD_ECUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -125,7 +139,8 @@ inline int make_tmap(CUtensorMap* m, const float* base, long long rows, int cols
     cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return LPD_ECUDA; }
     return LPD_OK;

@@ -72,18 +72,28 @@ col_stats_kernel(const float* __restrict__ z, long long rows, int C, int ld, dou
     block_reduce_cols(s1, s2, lane, lanes, g, C, active, partial + c0, blockIdx.x);
 }
 
-// ---- finalize: batch mean / biased var -> (scale, shift, mean, invstd), running-stat update ----------------------
-__global__ void bn_finalize_kernel(const double* __restrict__ partial, int nparts, double count, int C,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ out /* [4][C]: scale, shift, mean, invstd */) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// warp-cooperative fixed-order sum of partial[p * stride + off] over p: lane l takes p = l, l+32, ... then a shuffle tree
+// (the order is fixed by the launch geometry, so the result is deterministic)
+__device__ __forceinline__ double warp_sum_parts(const double* __restrict__ partial, int nparts, size_t stride, size_t off) {
+    const int lane = threadIdx.x & 31;
+    double s = 0;
+    for (int p = lane; p < nparts; p += 32) s += partial[(size_t)p * stride + off];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    return s;
+}
+
+// ---- finalize: batch mean / biased var -> (scale, shift, mean, invstd), running-stat update.  One warp per channel. ------
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ partial, int nparts, double count, int C,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                   float* __restrict__ out /* [4][C]: scale, shift, mean, invstd */) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c >= C) return;
-    double s1 = 0, s2 = 0;
-    for (int p = 0; p < nparts; ++p) {
-        s1 += partial[(size_t)p * 2 * C + c];
-        s2 += partial[(size_t)p * 2 * C + C + c];
-    }
+    const double s1 = warp_sum_parts(partial, nparts, (size_t)2 * C, c);
+    const double s2 = warp_sum_parts(partial, nparts, (size_t)2 * C, (size_t)C + c);
+    if ((threadIdx.x & 31) != 0) return;
     const double mean = s1 / count;
     double var = s2 / count - mean * mean;
     if (var < 0) var = 0;
@@ -100,13 +110,13 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partial, int npart
     }
 }
 
-// out[p] = sum over parts of partial[p][i]   (i < n), fp64 -> fp32
-__global__ void colsum_finalize_kernel(const double* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// out[i] = sum over parts of partial[p][i]   (i < n), fp64 -> fp32.  One warp per output.
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const double* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= n) return;
-    double s = 0;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n + i];
-    out[i] = (float)s;
+    const double s = warp_sum_parts(partial, nparts, (size_t)n, i);
+    if ((threadIdx.x & 31) == 0) out[i] = (float)s;
 }
 
 // ---- elementwise affine + activation: out = act(scale * z + shift) (GATE: aux * sigmoid) ---------------------------
@@ -469,7 +479,7 @@ extern "C" int lpd_bn_stats(const float* z, long long rows, int C, int ld, doubl
 extern "C" int lpd_bn_finalize(const double* partial, int nparts, double count, int C, const float* gamma, const float* beta,
                                float eps, float momentum, float* running_mean, float* running_var, float* bn_out, void* stream) {
     LPD_REQUIRE(partial && bn_out && nparts >= 1 && C >= 1 && count >= 1);
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partial, nparts, count, C, gamma, beta, eps, momentum,
+    bn_finalize_kernel<<<ceil_div(C, 8), 256, 0, as_stream(stream)>>>(partial, nparts, count, C, gamma, beta, eps, momentum,
                                                                       running_mean, running_var, bn_out);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
@@ -477,7 +487,7 @@ extern "C" int lpd_bn_finalize(const double* partial, int nparts, double count, 
 
 extern "C" int lpd_colsum_finalize(const double* partial, int nparts, int n, float* out, void* stream) {
     LPD_REQUIRE(partial && out && nparts >= 1 && n >= 1);
-    colsum_finalize_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(partial, nparts, n, out);
+    colsum_finalize_kernel<<<ceil_div(n, 8), 256, 0, as_stream(stream)>>>(partial, nparts, n, out);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }

@@ -165,6 +165,23 @@ def gemm_tf32(A, W, *, M, N, K, lda=None, out=None, ldc=None, scale=None, shift=
     return out
 
 
+def gemm_tf32_tn(A, Bm, *, M, N, K, lda, ldb, batch=1, out=None):
+    """out[z][m][n] = sum_{k<K} A[z*K+k][m] * Bm[z*K+k][n] on the tensor cores (TF32): contraction over the ROWS of two
+    point-major maps (weight gradients, NetVLAD aggregate).  -> [batch, M, N]"""
+    lib = _lib.load()
+    _f32(A, "A"), _f32(Bm, "B")
+    if out is None:
+        out = torch.empty(batch, M, N, device=A.device, dtype=torch.float32)
+    _call(f"lpd_gemm_tf32_tn[{M}x{N}x{K}x{batch}]", 1, lib.lpd_gemm_tf32_tn, A.data_ptr(), lda, Bm.data_ptr(), ldb, out.data_ptr(), N,
+          M * N, M, N, K, batch, _stream())
+    return out
+
+
+def _tn_ok(A, Bm, M, N, K, lda, ldb, batch):
+    return (_precision == "tf32" and M >= 64 and N >= 64 and N % 4 == 0 and lda % 4 == 0 and ldb % 4 == 0 and K >= 256
+            and (batch == 1 or K % 32 == 0) and A.data_ptr() % 16 == 0 and Bm.data_ptr() % 16 == 0)
+
+
 def linear(A, W, *, M, N, K, lda=None, out=None, ldc=None, scale=None, shift=None, act=ACT_NONE, slope=0.0):
     """conv1x1 / linear layer y = act(scale * (A . W^T) + shift) with W [N, K]; dispatches on the precision mode."""
     lda_ = K if lda is None else lda
@@ -452,15 +469,19 @@ def axpy(y, ldy, x, ldx, rows, C, alpha=1.0):
 def wgrad(dz, lddz, a, lda, rows, Nout, Kin, out=None):
     """dW[n][k] = sum_r dz[r][n] * a[r][k]  (weight gradient of z = a . W^T), split over the rows and reduced in a fixed
     order (deterministic).  -> [Nout, Kin]"""
-    tiles = ((Nout + 127) // 128) * ((Kin + 127) // 128)
+    bn = 256 if _precision == "tf32" else 128
+    tiles = ((Nout + 127) // 128) * ((Kin + bn - 1) // bn)
     want = max(1, min(512, (2 * SM_COUNT + tiles - 1) // tiles, rows // 256 if rows >= 256 else 1))
     splits = 1
     while splits * 2 <= want and rows % (splits * 2) == 0:
         splits *= 2
     per = rows // splits
     part = torch.empty(splits, Nout, Kin, device=dz.device, dtype=torch.float32)
-    gemm(dz, a, a_layout=A_KM, b_layout=B_KN, M=Nout, N=Kin, K=per, lda=lddz, ldb=lda, out=part, ldc=Kin,
-         batch=splits, strideA=per * lddz, strideB=per * lda, strideC=Nout * Kin)
+    if _tn_ok(dz, a, Nout, Kin, per, lddz, lda, splits):
+        gemm_tf32_tn(dz, a, M=Nout, N=Kin, K=per, lda=lddz, ldb=lda, batch=splits, out=part)
+    else:
+        gemm(dz, a, a_layout=A_KM, b_layout=B_KN, M=Nout, N=Kin, K=per, lda=lddz, ldb=lda, out=part, ldc=Kin,
+             batch=splits, strideA=per * lddz, strideB=per * lda, strideC=Nout * Kin)
     if splits == 1 and out is None:
         return part[0]
     res = splitk_reduce(part, splits, Nout, Kin)

@@ -22,6 +22,18 @@ from ._lib import LpdError
 A_MK, A_KM, B_NK, B_KN = ops.A_MK, ops.A_KM, ops.B_NK, ops.B_KN
 
 
+def dgrad(dz, lddz, w, rows, N, K, out=None, ldc=None, accumulate=False, tf32_ok=True):
+    """da[r][k] (+)= sum_n dz[r][n] * w[n][k]   (input gradient of z = a . w^T, w [N, K]).
+    In "tf32" precision mode the product runs on the tensor cores against a transposed copy of the (small) weight."""
+    if (tf32_ok and not accumulate and ops.get_precision() == "tf32" and N >= 32 and N % 4 == 0 and lddz % 4 == 0 and K >= 64
+            and K % 4 == 0 and rows >= 128 and (ldc is None or ldc % 4 == 0) and dz.data_ptr() % 16 == 0
+            and (out is None or out.data_ptr() % 16 == 0)):
+        wt = ops.transpose(w.unsqueeze(0))[0]                                   # [K, N]
+        return ops.gemm_tf32(dz, wt, M=rows, N=K, K=N, lda=lddz, out=out, ldc=ldc)
+    return ops.gemm(dz, w, a_layout=A_MK, b_layout=B_KN, M=rows, N=K, K=N, lda=lddz, ldb=K, out=out, ldc=ldc,
+                    act=ops.ACT_ADD if accumulate else ops.ACT_NONE, aux=out if accumulate else None)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # layer records
 # ----------------------------------------------------------------------------------------------------------------------
@@ -49,6 +61,7 @@ class Linear:
         self.weight, self.bias = weight, bias
         self.w = w2d(weight)
         self.N, self.K = self.w.shape
+        self.tf32_ok = tf32_ok
         lin = ops.linear if tf32_ok else ops.gemm
         return lin(a, self.w, M=rows, N=self.N, K=self.K, lda=lda, shift=None if bias is None else bias.detach())
 
@@ -61,10 +74,7 @@ class Linear:
             grads.add(self.bias, ops.colsum_finalize(part, nparts, 2 * self.N)[: self.N])
         if not need_da:
             return None
-        if da_out is None:
-            return ops.gemm(dz, self.w, a_layout=A_MK, b_layout=B_KN, M=self.rows, N=self.K, K=self.N, lda=lddz, ldb=self.K)
-        return ops.gemm(dz, self.w, a_layout=A_MK, b_layout=B_KN, M=self.rows, N=self.K, K=self.N, lda=lddz, ldb=self.K,
-                        out=da_out, ldc=ldda, act=ops.ACT_ADD if accumulate else ops.ACT_NONE, aux=da_out if accumulate else None)
+        return dgrad(dz, lddz, self.w, self.rows, self.N, self.K, out=da_out, ldc=ldda, accumulate=accumulate, tf32_ok=self.tf32_ok)
 
 
 def _bn_params(bn: nn.modules.batchnorm._BatchNorm):
@@ -191,8 +201,7 @@ class LPDNetTrain:
         dwpq3 = ops.wgrad(dpq3, 512, self.pyr[:, 128:], 512, M, 512, 128)          # [512, 128]
         grads.add(net.convSN1[0].weight, torch.cat((dwpq3[:256], dwpq3[256:]), 1))
         dx2 = dpyr[:, 128:]
-        ops.gemm(dpq3, self.wpq3, a_layout=A_MK, b_layout=B_KN, M=M, N=128, K=512, lda=512, ldb=128, out=dx2, ldc=512,
-                 act=ops.ACT_ADD, aux=dx2)
+        dgrad(dpq3, 512, self.wpq3, M, 512, 128, out=dx2, ldc=512, accumulate=True)
         del dpq3
         # ---- DG2: dense edge layer whose only consumer is the max ----------------------------------------------------
         S2 = ops.bn_bwd_sums(dx2, 512, self.zsel2, 128, M, 128, self.bn2e, act, slope)
@@ -200,8 +209,7 @@ class LPDNetTrain:
         grads.add(bn_dg2.bias, S2[0])
         grads.add(bn_dg2.weight, S2[1])
         grads.add(net.convDG2[0].weight, ops.wgrad(dz2e, 128, self.y1, 128, M * k, 128, 128))
-        dy1 = ops.gemm(dz2e, self.wdg2, a_layout=A_MK, b_layout=B_KN, M=M * k, N=128, K=128, lda=128, ldb=128,
-                       out=self.y1, ldc=128)                                       # y1 is dead after the wgrad: reuse it
+        dy1 = dgrad(dz2e, 128, self.wdg2, M * k, 128, 128, out=self.y1, ldc=128)   # y1 is dead after the wgrad: reuse it
         # ---- DG1: dense gradient from DG2 + arg-routed gradient of x1 -----------------------------------------------
         dpq1 = torch.empty(M, 256, device=dev, dtype=torch.float32)
         S1 = ops.edge_bwd(self.pq1, 256, self.pq1[:, 128:], 256, self.idx_f, B, N, k, 128, self.bn1e, act, slope, dpyr, 512,
@@ -210,7 +218,7 @@ class LPDNetTrain:
         grads.add(bn_dg1.weight, S1[1])
         dwpq1 = ops.wgrad(dpq1, 256, self.h2, 64, M, 256, 64)                      # [256, 64]
         grads.add(net.convDG1[0].weight, torch.cat((dwpq1[:128], dwpq1[128:]), 1))
-        dh2 = ops.gemm(dpq1, self.wpq1, a_layout=A_MK, b_layout=B_KN, M=M, N=64, K=256, lda=256, ldb=64)
+        dh2 = dgrad(dpq1, 256, self.wpq1, M, 256, 64)
         del dpq1, dy1, dpyr
         dz2 = self.b2.bwd(dh2, 64, grads)
         dh1 = self.l2.bwd(dz2, 64, grads)
@@ -236,12 +244,18 @@ class NetVLADTrain:
         self.f, self.B, self.M = f, B, M
         wc = nv.cluster_weights.detach()
         # soft assignment: a = softmax(BN(f . Wc))                                            :48-59
-        self.apre = ops.gemm(f, wc, a_layout=A_MK, b_layout=B_KN, M=M, N=K, K=D, lda=D, ldb=K)
+        if ops.get_precision() == "tf32" and M >= 128 and D % 4 == 0:
+            self.apre = ops.gemm_tf32(f, ops.transpose(wc.unsqueeze(0))[0], M=M, N=K, K=D)
+        else:
+            self.apre = ops.gemm(f, wc, a_layout=A_MK, b_layout=B_KN, M=M, N=K, K=D, lda=D, ldb=K)
         self.bn_a = BNAct()
         a = self.bn_a.fwd(self.apre, K, M, K, nv.bn1)
         self.a = ops.softmax64(a, M)
-        vraw = ops.gemm(f, self.a, a_layout=A_KM, b_layout=B_KN, M=D, N=K, K=N, lda=D, ldb=K, batch=B,
-                        strideA=N * D, strideB=N * K)                                         # :64-66 -> [B, D, K]
+        if ops._tn_ok(f, self.a, D, K, N, D, K, B):
+            vraw = ops.gemm_tf32_tn(f, self.a, M=D, N=K, K=N, lda=D, ldb=K, batch=B)          # :64-66 -> [B, D, K]
+        else:
+            vraw = ops.gemm(f, self.a, a_layout=A_KM, b_layout=B_KN, M=D, N=K, K=N, lda=D, ldb=K, batch=B,
+                            strideA=N * D, strideB=N * K)
         vraw = vraw.view(B, D, K)
         self.v, self.asum, self.n1, self.n2 = ops.netvlad_finish_train(vraw, self.a, nv.cluster_weights2.detach()[0].contiguous(),
                                                                        B, N, D, K)            # :61-74
@@ -290,10 +304,7 @@ class NetVLADTrain:
         dvraw, dasum, dwc2 = ops.netvlad_finish_bwd(dv, self.v, wc2, self.asum, self.n1, self.n2, B, D, K)
         grads.add(nv.cluster_weights2, dwc2)
         f, a = self.f, self.a
-        # vraw[b] = f[b]^T a[b]:  df[b] = a[b] . dvraw[b]^T ;  da[b] = f[b] . dvraw[b]
-        df = ops.gemm(a, dvraw, a_layout=A_MK, b_layout=B_NK, M=N, N=D, K=K, lda=K, ldb=K, batch=B,
-                      strideA=N * K, strideB=D * K, strideC=N * D,
-                      out=torch.empty(M, D, device=f.device, dtype=torch.float32), ldc=D)
+        # vraw[b] = f[b]^T a[b]:  da[b] = f[b] . dvraw[b] ;  df[b] = a[b] . dvraw[b]^T (accumulated below)
         da = ops.gemm(f, dvraw, a_layout=A_MK, b_layout=B_KN, M=N, N=K, K=D, lda=D, ldb=K, batch=B,
                       strideA=N * D, strideB=D * K, strideC=N * K,
                       out=torch.empty(M, K, device=f.device, dtype=torch.float32), ldc=K)
@@ -301,7 +312,14 @@ class NetVLADTrain:
         dapre = self.bn_a.bwd(ds, K, grads)
         wc = nv.cluster_weights.detach()
         grads.add(nv.cluster_weights, ops.wgrad(f, D, dapre, K, M, D, K))           # dWc[d][k] = sum_m f[m][d] dapre[m][k]
-        ops.gemm(dapre, wc, a_layout=A_MK, b_layout=B_NK, M=M, N=D, K=K, lda=K, ldb=K, out=df, ldc=D, act=ops.ACT_ADD, aux=df)
+        # df = dapre . Wc^T  (z = f . Wc  <=>  weight [N=K][K=D] = Wc^T, i.e. "w" of dgrad is Wc^T [K, D])
+        df = torch.empty(M, D, device=f.device, dtype=torch.float32)
+        if ops.get_precision() == "tf32" and M >= 128:
+            ops.gemm_tf32(dapre, wc, M=M, N=D, K=K, lda=K, out=df, ldc=D)           # Wc [D][K] is already K-contiguous
+        else:
+            ops.gemm(dapre, wc, a_layout=A_MK, b_layout=B_NK, M=M, N=D, K=K, lda=K, ldb=K, out=df, ldc=D)
+        ops.gemm(a, dvraw, a_layout=A_MK, b_layout=B_NK, M=N, N=D, K=K, lda=K, ldb=K, batch=B,
+                 strideA=N * K, strideB=D * K, strideC=N * D, out=df, ldc=D, act=ops.ACT_ADD, aux=df)
         return df
 
 

@@ -107,8 +107,11 @@ class NetVLADLoupe(nn.Module):
             a = ops.softmax64(ops.gemm_tf32(f, p["wct"], M=M, N=K, K=D, scale=p["s1"], shift=p["t1"]), M)
         else:
             a = ops.netvlad_assign(f, M, D, p["wc"], p["s1"], p["t1"], K)
-        vraw = ops.gemm(f, a, a_layout=ops.A_KM, b_layout=ops.B_KN, M=D, N=K, K=N, lda=D, ldb=K, batch=B,
-                        strideA=N * D, strideB=N * K)                                         # :64-66 -> [B, D, K]
+        if ops._tn_ok(f, a, D, K, N, D, K, B):
+            vraw = ops.gemm_tf32_tn(f, a, M=D, N=K, K=N, lda=D, ldb=K, batch=B)               # :64-66 -> [B, D, K]
+        else:
+            vraw = ops.gemm(f, a, a_layout=ops.A_KM, b_layout=ops.B_KN, M=D, N=K, K=N, lda=D, ldb=K, batch=B,
+                            strideA=N * D, strideB=N * K)
         if B == 1:
             vraw = vraw.view(1, D, K)
         v = ops.netvlad_finish(vraw, a, p["wc2"], B, N, D, K)                                 # :61-62,:68-74 -> [B, D*K]

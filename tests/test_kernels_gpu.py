@@ -254,6 +254,19 @@ def test_gemm_tf32_tensor_core_path(cuda, M, N, K, ldx):
     assert np.abs(strict.cpu().numpy() - got[:, 32:32 + N]).max() < 2.0 ** -9 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("M,N,K,batch,lda,ldb", [(1024, 64, 4096, 3, 1024, 64), (128, 128, 704, 5, 128, 128), (256, 64, 1000, 1, 256, 64),
+                                                  (1024, 512, 2048, 2, 1024, 512), (200, 72, 320, 2, 264, 80), (512, 128, 96, 4, 512, 512)])
+def test_gemm_tf32_tn_rows_contraction(cuda, M, N, K, batch, lda, ldb):
+    """lpd_gemm_tf32_tn: C[z] = A[zK:(z+1)K]^T . B[zK:(z+1)K] with MN-major UMMA operands -> 2^-9 of the result scale"""
+    r = rng(M + N + K + batch)
+    A = r.standard_normal((batch * K, lda)).astype(np.float32)
+    Bm = r.standard_normal((batch * K, ldb)).astype(np.float32)
+    got = ops.gemm_tf32_tn(dev(A), dev(Bm), M=M, N=N, K=K, lda=lda, ldb=ldb, batch=batch).cpu().numpy()
+    for z in range(batch):
+        ref = A[z * K:(z + 1) * K, :M].astype(np.float64).T @ Bm[z * K:(z + 1) * K, :N].astype(np.float64)
+        assert np.abs(got[z] - ref).max() < 2.0 ** -9 * np.abs(ref).max(), f"slice {z}"
+
+
 @pytest.mark.parametrize("B,N,k,C", [(2, 300, 20, 128), (1, 257, 32, 128), (1, 100, 7, 128), (2, 200, 20, 64), (1, 90, 25, 64), (3, 1024, 20, 128)])
 def test_edgeconv_dg_tensor_core_path(cuda, B, N, k, C):
     """lpd_edgeconv_dg_tf32: first layer exact fp32, second layer TF32 on tcgen05 -> 2^-9 of the layer-2 scale"""

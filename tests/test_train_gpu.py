@@ -112,3 +112,20 @@ def test_train_then_eval_roundtrip_and_loss_decreases(cuda):
     with torch.no_grad():
         out = model(x.cuda())
     assert torch.isfinite(out).all()
+
+
+def test_training_step_tf32_mode_close_to_fp32(cuda, golden):
+    """"tf32" precision mode (tensor-core GEMMs for the forward, input-gradient and weight-gradient products downstream
+    of the kNN inputs): loss within 2e-3 relative of the reference, gradient L2 norms within 2 % of the fp64 reference."""
+    g = golden("c3_train_step_n512_b2")
+    prev = ops.set_precision("tf32")
+    try:
+        model = build_train(512)
+        _, loss = run_step(model, synth.clouds(44, 512), 2)
+    finally:
+        ops.set_precision(prev)
+    ref = float(g["loss64"])
+    assert abs(float(loss.detach()) - ref) <= 2e-3 * abs(ref)
+    for key, p in model.named_parameters():
+        gn, rn = float(p.grad.double().norm()), float(g["gnorm64." + key])
+        assert abs(gn - rn) <= 2e-2 * rn, f"{key}: {gn} vs {rn}"
