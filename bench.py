@@ -301,6 +301,186 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ======================================================================================================================
+# C3: LPD-Net training step (train-mode forward, lazy quadruplet loss, backward, gradient all-reduce, Adam)
+# ======================================================================================================================
+TRAIN_METRIC = "LPD-Net training-step throughput (featnet=lpdnet, 4096 pts, lazy quadruplet loss, batch_num_queries=2 per GPU, Adam)"
+TRAIN_BQ, TRAIN_P, TRAIN_NN = 2, 2, 18
+TRAIN_CLOUDS = TRAIN_BQ * (1 + TRAIN_P + TRAIN_NN + 1)      # 44 clouds per GPU per step
+
+
+def synth_tuples(seed: int):
+    """one batch of training tuples in the reference's DataLoader layout (host tensors)"""
+    import torch
+    from lpdnet_b200 import synth
+    x = synth.clouds(TRAIN_CLOUDS, NPTS, seed=seed).view(TRAIN_BQ, 1 + TRAIN_P + TRAIN_NN + 1, NPTS, 3)
+    return tuple(t.contiguous() for t in torch.split(x, [1, TRAIN_P, TRAIN_NN, 1], dim=1))
+
+
+def cpu_baseline_train(n_tuples: int, threads: int):
+    """Times the differentiable CPU oracle (oracle/model_torch.py: the reference's as-written forward + torch autograd +
+    the same loss) on `n_tuples` tuples of 22 clouds.  Returns (submaps/s, seconds)."""
+    import torch
+    from lpdnet_b200 import synth
+    from lpdnet_b200.util.PointNetVlad import PointNetVlad
+    from oracle import model_torch
+    torch.set_num_threads(threads)
+    shapes = {k: v.shape for k, v in PointNetVlad(num_points=NPTS, featnet="lpdnet", emb_dims=1024).state_dict().items()}
+    sd = synth.fill_state_dict(shapes)
+    x = synth.clouds(22 * n_tuples, NPTS)
+    t0 = time.perf_counter()
+    _, loss, grads, _ = model_torch.train_step(sd, x, n_tuples)
+    dt = time.perf_counter() - t0
+    assert bool(torch.isfinite(loss)) and len(grads) > 20
+    return 22 * n_tuples / dt, dt
+
+
+def run_reference_train(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        cpu_baseline_train(1, threads)
+        n += 22
+    dt = time.perf_counter() - t0
+    v = n / dt
+    line = {"impl": "reference", "metric": TRAIN_METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3: LPD-Net training step, 4096-pt submaps", "step": "1 tuple (22 submaps) per step on the host CPU: forward + loss + autograd backward (bounded sample of the 44-submap step; no optimizer step)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"22 submaps/step x {args.steps} steps, torch-CPU oracle of the reference's as-written training forward/backward"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_train(args):
+    import torch
+    import torch.distributed as dist
+    from lpdnet_b200 import ops, optim, synth
+    from lpdnet_b200 import train_pointnetvlad as TP
+    from lpdnet_b200.util.PointNetVlad import PointNetVlad
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU oracle")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    ops.set_precision(args.precision)
+    torch.manual_seed(1234)
+    model = PointNetVlad(num_points=NPTS, featnet="lpdnet", emb_dims=1024)
+    model.load_state_dict(synth.synthetic_state_dict(model))          # identical replicas on every rank
+    model = model.to(device).train()
+    # lr 1e-5 (reference default 1e-3 drives this synthetic tuple's hinge loss to exactly 0 within a few steps, which would
+    # make every gradient zero; the work per step is data-independent either way)
+    opt = optim.Adam(model.parameters(), lr=1e-5)
+    n_rot = 4
+    host = [tuple(t.pin_memory() for t in synth_tuples(4321 + 131 * rank + i)) for i in range(n_rot)]
+    dev_in = [tuple(t.to(device) for t in h) for h in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def step(batch):
+        return TP.train_step(model, opt, *batch, margin_1=0.5, margin_2=0.2)
+
+    for i in range(max(args.warmup, 3)):
+        loss = step(dev_in[i % n_rot])
+    barrier()
+    ops.reset_launch_count()
+    evs = []
+    with ClockSampler(local) as clk:
+        barrier()
+        for i in range(args.steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            loss = step(dev_in[i % n_rot])
+            e.record()
+            evs.append((s, e))
+        barrier()
+    launches = ops.launch_count()
+    t = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t)
+    value = world * TRAIN_CLOUDS * args.steps / (t_ms * 1e-3)
+    last_loss = float(loss)
+
+    # ---- end to end: pinned host tuples -> H2D -> step -> loss value back on the host, every step ----
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(args.steps):
+        loss_host = float(step(host[i % n_rot]))
+    e.record()
+    barrier()
+    te = torch.tensor([s.elapsed_time(e)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * TRAIN_CLOUDS * args.steps / (float(te) * 1e-3)
+
+    roofline, breakdown = None, None
+    if rank == 0:
+        peaks = load_peaks()
+        per = {}
+        nprof = 2
+        for i in range(nprof):
+            flush.zero_()
+            ops.profile(True)
+            step(dev_in[i % n_rot])
+            rec = ops.profile(False)
+            torch.cuda.synchronize(device)
+            for label, a, b in rec:
+                per.setdefault(label, []).append(a.elapsed_time(b))
+        tot = {k_: sum(v) / nprof for k_, v in per.items()}
+        cnt = {k_: len(v) / nprof for k_, v in per.items()}
+        step_ms = sum(tot.values())
+        breakdown = {k_: {"ms_per_step": round(v, 4), "share": round(v / step_ms, 4), "launches": cnt[k_]}
+                     for k_, v in sorted(tot.items(), key=lambda kv: -kv[1])[:24]}
+        top = max(tot, key=tot.get)
+        work = kernel_work(top, TRAIN_CLOUDS)
+        if work is not None:
+            flops, byts = work
+            per_launch_ms = tot[top] / cnt[top]
+            tf = flops / (per_launch_ms * 1e-3) / 1e12
+            roofline = {"kernel": top, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained",
+                        "share_of_step": tot[top] / step_ms, "ms_per_launch": per_launch_ms}
+        threads = os.cpu_count() or 1
+        cpu_v, cpu_t = cpu_baseline_train(1, threads)
+        nparams = sum(p.numel() for p in model.parameters())
+        line = {"metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+                "config": {"workload": "C3: LPD-Net training step (train-mode forward, lazy quadruplet loss m1=0.5 m2=0.2, backward, "
+                                       "gradient all-reduce, fused Adam)",
+                           "precision": args.precision, "submaps_per_gpu_per_step": TRAIN_CLOUDS, "tuples_per_gpu": TRAIN_BQ, "points": NPTS,
+                           "sharding": f"whole tuples per GPU (dp{world}), per-rank BatchNorm statistics, one NCCL all-reduce of the flat fp32 gradient buffer ({4 * nparams / 1e6:.1f} MB) per step",
+                           "l2": "256 MiB memset between timed steps (untimed); 4 rotating tuple batches", "last_loss": last_loss},
+                "clocks": clk.result, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TRAIN_CLOUDS * NPTS * 3 * 4, "d2h_bytes_per_step": 4,
+                        "api": "lpdnet_b200.train_pointnetvlad.train_step (pinned host tuples -> loss value on the host)", "last_loss": loss_host},
+                "roofline": roofline, "kernel_breakdown": breakdown,
+                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": f"1 tuple (22 submaps) forward+loss+backward in {cpu_t:.1f} s, torch-CPU oracle of the reference's as-written training path"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -310,9 +490,14 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
                     help="tf32: dense layers on tcgen05 tensor cores (descriptor error vs the reference measured <= 1e-4); "
                          "fp32: every layer in strict fp32 FFMA arithmetic")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 (default, the configuration BASELINE.json's metric is quoted on): eval embedding of 64 submaps per GPU; "
+                         "c3: training step on 2 tuples = 44 submaps per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_train if args.workload == "c3" else run_reference)(args)
+    elif args.workload == "c3":
+        run_train(args)
     else:
         run_ours(args)
 

@@ -227,6 +227,12 @@ int lpd_retrieval_topk(const float* db, int Ndb, const float* q, int Nq, int D, 
                        int idx_offset, int32_t* idx, double* dist,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Merge `lists` sorted top-k lists per query (part_dist / part_idx [lists][Nq][k], GLOBAL database indices, -1 = empty
+ * slot) into one: ascending distance, ties to the lower index — the merge step of the database-sharded search (each
+ * rank's lpd_retrieval_topk list, all-gathered over NCCL). */
+int lpd_topk_merge(const double* part_dist, const int32_t* part_idx, int lists, int Nq, int k,
+                   int32_t* idx, double* dist, void* stream);
+
 /* =============================================================================================
  * TRAIN MODE (reference: model.train() forward, loss.backward(), optimizer.step();
  * train_pointnetvlad.py:121-130,150-159).  Batch-statistics BatchNorm and the backward pass.

@@ -151,7 +151,7 @@ retrieval_merge_kernel(const double* __restrict__ part_val, const int* __restric
         const size_t o = ((size_t)s * Nq + row) * k + lane;
         const double v = lane < k ? part_val[o] : INFINITY;
         const int j = lane < k ? part_idx[o] : INT_MAX;
-        unsigned mask = __ballot_sync(kFull, lane < k && j != INT_MAX);
+        unsigned mask = __ballot_sync(kFull, lane < k && j != INT_MAX && j >= 0);   // INT_MAX / -1 = empty slot
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -210,6 +210,15 @@ extern "C" int lpd_retrieval_topk(const float* db, int Ndb, const float* q, int 
                                                                                    part_val, part_idx);
     LPD_LAUNCH_CHECK();
     retrieval_merge_kernel<<<ceil_div(Nq, 8), 256, 0, st>>>(part_val, part_idx, used_splits, Nq, k, idx_offset, idx, dist);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+extern "C" int lpd_topk_merge(const double* part_dist, const int32_t* part_idx, int lists, int Nq, int k,
+                              int32_t* idx, double* dist, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(part_dist && part_idx && idx && lists >= 1 && Nq >= 1 && k >= 1 && k <= 32);
+    retrieval_merge_kernel<<<ceil_div(Nq, 8), 256, 0, as_stream(stream)>>>(part_dist, part_idx, lists, Nq, k, 0, idx, dist);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }

@@ -282,6 +282,18 @@ def retrieval_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_offset: int = 
     return idx, dist
 
 
+def topk_merge(part_dist: torch.Tensor, part_idx: torch.Tensor):
+    """part_dist float64 / part_idx int32 [lists, Nq, k] (global indices, -1 = empty) -> (idx [Nq, k], dist [Nq, k])"""
+    lib = _lib.load()
+    lists, Nq, k = part_idx.shape
+    part_dist, part_idx = part_dist.contiguous(), part_idx.contiguous()
+    idx = torch.empty(Nq, k, device=part_idx.device, dtype=torch.int32)
+    dist = torch.empty(Nq, k, device=part_idx.device, dtype=torch.float64)
+    _call("lpd_topk_merge", 1, lib.lpd_topk_merge, part_dist.data_ptr(), part_idx.data_ptr(), lists, Nq, k, idx.data_ptr(),
+          dist.data_ptr(), _stream())
+    return idx, dist
+
+
 # =====================================================================================================================
 # train mode: batch-statistics BatchNorm, backward kernels, Adam (include/lpd_b200.h, "TRAIN MODE")
 # =====================================================================================================================

@@ -124,3 +124,25 @@ def test_recall_oracle_matches_reference_kdtree(golden):
                 assert abs(float(np.sum(sims)) - g["sim_sum"][p]) < 1e-4
             p += 1
     assert 50.0 < g["recall"][:, 0].mean() < 95.0  # the fixture is not a trivial 100 % identity check
+
+
+def test_torch_training_oracle_reproduces_reference_autograd(golden):
+    """oracle/model_torch.py (the differentiable restatement used as CPU baseline / gradient oracle) against the reference's
+    own train-mode outputs, loss, parameter gradients and running statistics (tests/golden/c3_train_step_n256)."""
+    import torch
+    from lpdnet_b200 import synth
+    from lpdnet_b200.util.PointNetVlad import PointNetVlad
+    from oracle import model_torch
+    g = golden("c3_train_step_n256")
+    sd = synth.synthetic_state_dict(PointNetVlad(num_points=256, featnet="lpdnet", emb_dims=1024))
+    out, loss, grads, stats = model_torch.train_step(sd, synth.clouds(22, 256), 1)
+    assert np.abs(out.numpy() - g["out"]).max() <= 1e-6
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert len(grads) == 28
+    for key, gr in grads.items():
+        flat = gr.reshape(-1)
+        sub = flat[::max(1, flat.numel() // 4096)][:4096].numpy()
+        ref = g["grad." + key]
+        assert np.abs(sub - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-12), key
+    for key, v in stats.items():
+        assert np.allclose(v.numpy(), g["after." + key], rtol=1e-5, atol=1e-6), key
