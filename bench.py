@@ -384,9 +384,10 @@ def run_train(args):
     model = PointNetVlad(num_points=NPTS, featnet="lpdnet", emb_dims=1024)
     model.load_state_dict(synth.synthetic_state_dict(model))          # identical replicas on every rank
     model = model.to(device).train()
-    # lr 1e-5 (reference default 1e-3 drives this synthetic tuple's hinge loss to exactly 0 within a few steps, which would
-    # make every gradient zero; the work per step is data-independent either way)
-    opt = optim.Adam(model.parameters(), lr=1e-5)
+    # lr 1e-7: with the reference's default 1e-3 (or even 1e-5) Adam drives the hinge loss of these 4 synthetic tuple batches
+    # to exactly 0 within ~10 steps and every gradient becomes zero; the kernels do the same work either way (nothing is
+    # data-dependent), but a tiny lr keeps the loss and gradients non-trivial for the whole timed region.
+    opt = optim.Adam(model.parameters(), lr=1e-7)
     n_rot = 4
     host = [tuple(t.pin_memory() for t in synth_tuples(4321 + 131 * rank + i)) for i in range(n_rot)]
     dev_in = [tuple(t.to(device) for t in h) for h in host]
