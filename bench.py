@@ -168,7 +168,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{sample} submaps/step x {args.steps} steps, numpy+C oracle of the reference's as-written forward"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -295,7 +295,7 @@ def run_ours(args):
                 "roofline": roofline, "kernel_breakdown": breakdown,
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
                                  "sample": f"{threads} submaps (of the 64-submap batch) in {cpu_t:.1f} s, one per core, numpy oracle of the reference's as-written forward"}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -353,7 +353,7 @@ def run_reference_train(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"22 submaps/step x {args.steps} steps, torch-CPU oracle of the reference's as-written training forward/backward"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_train(args):
@@ -433,18 +433,20 @@ def run_train(args):
     e2e_value = world * TRAIN_CLOUDS * args.steps / (float(te) * 1e-3)
 
     roofline, breakdown = None, None
+    # per-kernel device time of a step: every rank runs these steps (the gradient all-reduce inside optimizer.step() is a
+    # collective), only rank 0 records
+    per = {}
+    nprof = 2
+    for i in range(nprof):
+        flush.zero_()
+        ops.profile(rank == 0)
+        step(dev_in[i % n_rot])
+        rec = ops.profile(False)
+        torch.cuda.synchronize(device)
+        for label, a, b in (rec or []):
+            per.setdefault(label, []).append(a.elapsed_time(b))
     if rank == 0:
         peaks = load_peaks()
-        per = {}
-        nprof = 2
-        for i in range(nprof):
-            flush.zero_()
-            ops.profile(True)
-            step(dev_in[i % n_rot])
-            rec = ops.profile(False)
-            torch.cuda.synchronize(device)
-            for label, a, b in rec:
-                per.setdefault(label, []).append(a.elapsed_time(b))
         tot = {k_: sum(v) / nprof for k_, v in per.items()}
         cnt = {k_: len(v) / nprof for k_, v in per.items()}
         step_ms = sum(tot.values())
@@ -476,10 +478,32 @@ def run_train(args):
                 "roofline": roofline, "kernel_breakdown": breakdown,
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
                                  "sample": f"1 tuple (22 submaps) forward+loss+backward in {cpu_t:.1f} s, torch-CPU oracle of the reference's as-written training path"}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) print to stdout; the contract is ONE JSON line there.  Point fd 1 at
+    stderr for the whole run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -495,6 +519,7 @@ def main():
                     help="c2 (default, the configuration BASELINE.json's metric is quoted on): eval embedding of 64 submaps per GPU; "
                          "c3: training step on 2 tuples = 44 submaps per GPU")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         (run_reference_train if args.workload == "c3" else run_reference)(args)
     elif args.workload == "c3":
