@@ -97,6 +97,14 @@ size_t lpd_knn_workspace_bytes(int B, int N, int C, int k);
 int lpd_knn_tc(const float* x, int B, int N, int C, int k, void* idx, int idx_i64,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same result as lpd_knn (bit-identical canonical order) for C == 3 (Cartesian kNN, lpdnet_model.py:255): a uniform grid
+ * over the cloud decides which candidates are scored (cells in growing shells around the query, pruned with a bound that
+ * covers the fp32 rounding of the canonical score), every scored candidate uses the canonical arithmetic and order.
+ * x [B][N][3]; workspace >= lpd_knn_xyz_workspace_bytes(B, N) bytes, 16-byte aligned. */
+size_t lpd_knn_xyz_workspace_bytes(int B, int N);
+int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes,
+                void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * General fp32 GEMM with fused per-column affine + activation epilogue (CUDA-core FFMA path,
  * "strict" fp32 arithmetic):

@@ -90,6 +90,8 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
 # C == 64: exact filter-and-refine kNN with the gram tiles on tcgen05 (lpd_knn_tc, 3xTF32 + canonical re-score).
 # Bit-identical to the CUDA-core kernel; rows whose candidate list cannot be proven complete are recomputed by it.
 KNN_TENSOR_CORES = True
+# C == 3: exact grid-accelerated kNN (lpd_knn_xyz); bit-identical to the brute-force scan of lpd_knn.
+KNN_GRID = True
 
 
 def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
@@ -104,6 +106,11 @@ def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
         ws = torch.empty((nbytes + 3) // 4, device=x_pm.device, dtype=torch.float32)
         _call(f"lpd_knn_tc[C={Cc},k={k}]", 4, lib.lpd_knn_tc, x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64),
               ws.data_ptr(), ws.numel() * 4, _stream())
+    elif KNN_GRID and Cc == 3 and N >= 64:
+        nbytes = lib.lpd_knn_xyz_workspace_bytes(B, N)
+        ws = torch.empty((nbytes + 3) // 4, device=x_pm.device, dtype=torch.float32)
+        _call(f"lpd_knn_xyz[k={k}]", 2, lib.lpd_knn_xyz, x_pm.data_ptr(), B, N, k, idx.data_ptr(), int(int64), ws.data_ptr(),
+              ws.numel() * 4, _stream())
     else:
         _call(f"lpd_knn[C={Cc},k={k}]", 1, lib.lpd_knn, x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64), _stream())
     return idx

@@ -44,6 +44,41 @@ def test_knn_exact_ties_and_duplicates(cuda):
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("kind", ["clustered", "planar", "offset", "line", "identical", "lattice16", "outliers", "tiny"])
+@pytest.mark.parametrize("k", [20, 7, 32])
+def test_knn_xyz_grid_is_bit_exact_on_adversarial_clouds(cuda, kind, k):
+    """lpd_knn_xyz (grid-pruned search) must return exactly the canonical lists whatever the point distribution: the grid
+    only prunes, with a bound that covers the fp32 rounding of the canonical score."""
+    r = rng(len(kind) * 7 + k)
+    N = 2048
+    if kind == "clustered":        # LiDAR-like: dense blobs + sparse background
+        x = np.concatenate([r.normal(c, 0.01, (400, 3)) for c in r.uniform(-1, 1, (4, 3))] + [r.uniform(-1, 1, (N - 1600, 3))])
+    elif kind == "planar":         # ground plane: z extent ~ 0
+        x = np.concatenate([r.uniform(-1, 1, (N, 2)), r.normal(0, 1e-4, (N, 1))], 1)
+    elif kind == "offset":         # far from the origin: the expansion -xx + 2dot - xx cancels heavily
+        x = r.uniform(-1, 1, (N, 3)) + np.array([100.0, -50.0, 25.0])
+    elif kind == "line":           # degenerate extent on two axes
+        x = np.concatenate([r.uniform(-1, 1, (N, 1)), np.zeros((N, 2))], 1)
+    elif kind == "identical":      # every point the same: all ties, order = index
+        x = np.tile(r.uniform(-1, 1, (1, 3)), (N, 1))
+    elif kind == "lattice16":      # masses of exact ties across cell boundaries
+        g = np.arange(16.0) / 8 - 1
+        x = np.stack(np.meshgrid(g, g, g[:8], indexing="ij"), -1).reshape(-1, 3)
+    elif kind == "outliers":       # a few far points stretch the bounding box: almost everything lands in one cell
+        x = np.concatenate([r.uniform(-0.01, 0.01, (N - 4, 3)), r.uniform(-50, 50, (4, 3))])
+    else:                          # N below the grid path threshold and below L
+        x = r.uniform(-1, 1, (70, 3))
+    x = x.astype(np.float32)[None]
+    want = knn_canonical(x, k)
+    got = ops.knn(dev(x), k).cpu().numpy()
+    assert np.array_equal(got, want)
+    prev, ops.KNN_GRID = ops.KNN_GRID, False
+    try:
+        assert np.array_equal(ops.knn(dev(x), k).cpu().numpy(), want)       # brute-force kernel: same lists
+    finally:
+        ops.KNN_GRID = prev
+
+
 def test_knn_matches_reference_golden_sets(cuda, golden):
     """against the reference's own torch knn() output (tie-aware: sets may differ only on near-ties)"""
     from _helpers import assert_knn_equivalent
