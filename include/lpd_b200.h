@@ -105,6 +105,14 @@ size_t lpd_knn_xyz_workspace_bytes(int B, int N);
 int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes,
                 void* stream);
 
+/* Spatial (grid-cell) order of every cloud: perm[b][t] = original index of the t-th point in cell order (stable inside a
+ * cell, so it is a pure function of the cloud), inv (nullable) = the inverse permutation, xyz_sorted (nullable) = the
+ * coordinates in that order.  Every per-point stage of the path is permutation-equivariant and NetVLAD sums over the
+ * points (PointNetVlad.py:61-66), so the host modules run each cloud in this order for memory locality.
+ * workspace >= lpd_knn_xyz_workspace_bytes(B, N). */
+int lpd_cell_order(const float* x, int B, int N, int32_t* perm, int32_t* inv, float* xyz_sorted,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * General fp32 GEMM with fused per-column affine + activation epilogue (CUDA-core FFMA path,
  * "strict" fp32 arithmetic):

@@ -7,21 +7,24 @@
 //                                                        B = Y1 (N = up to 128 edge rows = TMEM columns), K = C1
 // so one TMEM lane holds one output channel and the k edges of a point are k consecutive accumulator columns.
 //
-// Persistent CTA, 13 warps:
+// Persistent CTA, 16 warps (512 threads -> 128 registers per thread):
 //   warps 0-3   epilogue: tcgen05.ld 32 columns at a point's first edge, folded BN + activation, max over its k
 //               columns in registers, 128-byte coalesced store of x2 (lane = channel)
-//   warp  4     TMA load of W2 (128B-swizzled K-major k-blocks), TMEM allocation, single-thread tcgen05.mma issue
-//   warps 5-12  producers: per point gather the k neighbour rows of P (L2-resident), y1 = act(s1 * (p_j + q_i) + t1)
-//               in fp32, running max -> x1, and st.shared of y1 rows straight into the 128B-swizzled UMMA layout
-//               (double-buffered; generic-proxy writes are fenced to the async proxy before the mbarrier arrive)
+//   warps 4-15  producers, two groups of 6; the first warp of a group also loads W2 by TMA (group 0), owns the TMEM
+//               allocation (group 0) and is the single-thread tcgen05.mma issuer of its group's stage;
+//               two groups of 6 (group g fills shared-memory stage g, i.e. the CTA's even / odd tiles, so both
+//               stages are gathered concurrently): per point gather the k neighbour rows of P (L2-resident, 10 rows in
+//               flight per lane), y1 = act(s1 * (p_j + q_i) + t1) in fp32, running max -> x1, and st.shared of y1 rows
+//               straight into the 128B-swizzled UMMA layout (generic-proxy writes are fenced to the async proxy before the
+//               mbarrier arrive).  The gather is L2-latency bound: what matters is the number of rows in flight per SM.
 #include "tc_common.cuh"
 
 namespace lpd {
 namespace tc {
 
-constexpr int DG_EPI_WARPS = 4, DG_PROD_WARPS = 8;
-constexpr int DG_MMA_WARP = DG_EPI_WARPS;
-constexpr int DG_THREADS = 32 * (DG_EPI_WARPS + 1 + DG_PROD_WARPS);
+constexpr int DG_EPI_WARPS = 4, DG_PROD_WARPS = 12, DG_GROUP_WARPS = DG_PROD_WARPS / 2;
+constexpr int DG_ALLOC_WARP = DG_EPI_WARPS;      // first producer warp of group 0
+constexpr int DG_THREADS = 32 * (DG_EPI_WARPS + DG_PROD_WARPS);
 constexpr int DG_ROWS = 128;          // operand tile rows (both W2 and the edge tile)
 constexpr int DG_ACC_STRIDE = 256;    // TMEM columns between the two accumulator stages
 
@@ -63,12 +66,12 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
         reinterpret_cast<uint4*>(y_s)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
-    if (warp == DG_MMA_WARP) {
+    if (warp == DG_ALLOC_WARP) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w2)) : "memory");
             mbar_init(wfull, 1);
             for (int s = 0; s < 2; ++s) {
-                mbar_init(&yfull[s], DG_PROD_WARPS);
+                mbar_init(&yfull[s], DG_GROUP_WARPS);
                 mbar_init(&yempty[s], 1);
                 mbar_init(&tfull[s], 1);
                 mbar_init(&tempty[s], DG_EPI_WARPS);
@@ -84,43 +87,27 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == DG_MMA_WARP) {
-        if (lane == 0) {
-            mbar_expect_tx(wfull, OP_BYTES);
-            for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_s + kb * KB_BYTES, &tmap_w2, wfull, kb * 32, 0);
-            mbar_wait(wfull, 0);
-            const uint32_t idesc = make_idesc(128, P.n_mma);
-            const uint32_t w_addr = smem_u32(w_s);
-            long long t = blockIdx.x;
-            for (uint32_t it = 0; t < P.num_tiles; t += gridDim.x, ++it) {
-                const uint32_t s = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(&tempty[s], ph ^ 1);
-                mbar_wait(&yfull[s], ph);
-                tc_fence_after();
-                const uint32_t y_addr = smem_u32(y_s + s * OP_BYTES);
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint64_t da = make_smem_desc(w_addr + kb * KB_BYTES), db = make_smem_desc(y_addr + kb * KB_BYTES);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        tc_mma_tf32(tmem_base + s * DG_ACC_STRIDE, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc,
-                                    (kb | ks) != 0 ? 1u : 0u);
-                }
-                tc_commit(&yempty[s]);
-                tc_commit(&tfull[s]);
-            }
-        }
-    } else if (warp > DG_MMA_WARP) {
+    if (warp >= DG_EPI_WARPS) {
         // ------------------------------ producers ------------------------------
-        const int pw = warp - DG_MMA_WARP - 1;
+        const int pw = (warp - DG_EPI_WARPS) % DG_GROUP_WARPS;      // this warp's first point inside a tile
+        const int grp = (warp - DG_EPI_WARPS) / DG_GROUP_WARPS;     // = the shared-memory / TMEM stage this warp fills
+        const bool issuer = pw == 0;                                // this warp's lane 0 issues the group's MMAs
+        if (warp == DG_ALLOC_WARP && lane == 0) {
+            mbar_expect_tx(wfull, OP_BYTES);
+            for (int kb2 = 0; kb2 < KB; ++kb2) tma_load_2d(w_s + kb2 * KB_BYTES, &tmap_w2, wfull, kb2 * 32, 0);
+        }
+        const uint32_t idesc = make_idesc(128, P.n_mma);
+        const uint32_t w_addr = smem_u32(w_s);
+        bool w_ready = false;
         const int sr = lane / LPR, lc = lane % LPR;    // sub-row of this lane within the iteration, 16-byte chunk index
         const int kb = lc >> 3, chunk = lc & 7;
         float s1[4], t1[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) { s1[u] = __ldg(P.s1 + lc * 4 + u); t1[u] = __ldg(P.t1 + lc * 4 + u); }
-        long long t = blockIdx.x;
-        // software pipeline: the neighbour list and centre row of this warp's first point of the NEXT tile are
-        // requested before waiting for the current stage, so the idx -> gather dependency is off the critical path
+        const long long tstep = 2LL * gridDim.x;       // this group's tiles: every other tile of the CTA
+        long long t = blockIdx.x + (long long)grp * gridDim.x;
+        // software pipeline: the neighbour list and centre row of this warp's first point of its NEXT tile are
+        // requested before waiting for the stage, so the idx -> gather dependency is off the critical path
         int nj = 0;
         float4 nq = make_float4(0.f, 0.f, 0.f, 0.f);
         auto prefetch = [&](long long tile) {
@@ -131,14 +118,14 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
             }
         };
         prefetch(t);
-        for (uint32_t it = 0; t < P.num_tiles; t += gridDim.x, ++it) {
-            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+        uint8_t* ys = y_s + grp * OP_BYTES + kb * KB_BYTES;
+        for (uint32_t it = 0; t < P.num_tiles; t += tstep, ++it) {
+            const uint32_t ph = it & 1;
             const int cj = nj;
             const float4 cq = nq;
-            prefetch(t + gridDim.x);
-            mbar_wait(&yempty[s], ph ^ 1);
-            uint8_t* ys = y_s + s * OP_BYTES + kb * KB_BYTES;
-            for (int pl = pw; pl < PTS; pl += DG_PROD_WARPS) {
+            prefetch(t + tstep);
+            mbar_wait_sleep(&yempty[grp], ph ^ 1);
+            for (int pl = pw; pl < PTS; pl += DG_GROUP_WARPS) {
                 const long long pt = t * PTS + pl;
                 if (pt >= P.total_pts) break;
                 const long long cloud0 = (pt / P.N) * P.N;
@@ -149,7 +136,7 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
                     myj = (lane < k) ? __ldg(P.idx + pt * k + lane) : 0;
                 }
                 float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                constexpr int U = 8;                  // gathers in flight per lane
+                constexpr int U = 10;                 // gathers in flight per lane
                 for (int m0 = 0; m0 < k; m0 += U * RPI) {
                     float4 pv[U];
 #pragma unroll
@@ -184,34 +171,85 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&yfull[s]);
+            if (lane == 0) {
+                mbar_arrive(&yfull[grp]);
+                if (issuer) {
+                    // all six producer warps of the group run in lockstep on equal work, so this wait is short
+                    if (!w_ready) { mbar_wait(wfull, 0); w_ready = true; }
+                    mbar_wait_sleep(&tempty[grp], ph ^ 1);
+                    mbar_wait_sleep(&yfull[grp], ph);
+                    tc_fence_after();
+                    const uint32_t y_addr = smem_u32(y_s + grp * OP_BYTES);
+#pragma unroll
+                    for (int kb2 = 0; kb2 < KB; ++kb2) {
+                        const uint64_t da = make_smem_desc(w_addr + kb2 * KB_BYTES), db = make_smem_desc(y_addr + kb2 * KB_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            tc_mma_tf32(tmem_base + grp * DG_ACC_STRIDE, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc,
+                                        (kb2 | ks) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&yempty[grp]);
+                    tc_commit(&tfull[grp]);
+                }
+            }
+            __syncwarp();
         }
     } else {
         // ------------------------------ epilogue ------------------------------
+        // BN (scale s2, shift t2) and the activation are monotone per channel, and a lane owns ONE channel, so
+        //     max_m act(s2 * d_m + t2) = act(s2 * ext_m d_m + t2),  ext = max if s2 >= 0 else min            (exact in fp32)
+        // -> the per-edge work is a bare min/max over the k accumulator columns of the point (3-input FMNMX on sm_100).
         const int ch = warp * 32 + lane;               // output channel = TMEM lane
         const bool ch_ok = ch < P.C2;
         const float s2 = ch_ok ? __ldg(P.s2 + ch) : 0.f, t2 = ch_ok ? __ldg(P.t2 + ch) : 0.f;
         long long t = blockIdx.x;
         for (uint32_t it = 0; t < P.num_tiles; t += gridDim.x, ++it) {
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
-            mbar_wait(&tfull[s], ph);
+            mbar_wait_sleep(&tfull[s], ph);
             tc_fence_after();
             if (warp * 32 < P.C2) {
                 for (int pl = 0; pl < PTS; ++pl) {
                     const long long pt = t * PTS + pl;
                     if (pt >= P.total_pts) break;
-                    uint32_t r[32];
-                    tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + s * DG_ACC_STRIDE + pl * k, r);
-                    // four independent max chains (a single chain is a 32-deep dependent sequence)
-                    float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + s * DG_ACC_STRIDE + pl * k;
+                    float mx, mn;
+                    if (k == 20) {                      // the reference's k: exactly 16 + 4 columns, no masking
+                        uint32_t r[20];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                            : "r"(taddr));
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(taddr + 16));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float a4[4], b4[4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = fmaf(s2, __uint_as_float(r[j]), t2);
-                        v = fmaxf(v, v * P.neg_slope);
-                        b4[j & 3] = fmaxf(b4[j & 3], j < k ? v : -INFINITY);
+                        for (int u = 0; u < 4; ++u) { a4[u] = __uint_as_float(r[u]); b4[u] = a4[u]; }
+#pragma unroll
+                        for (int j = 4; j < 20; j += 2) {
+                            const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+                            a4[(j >> 1) & 3] = fmaxf(fmaxf(a4[(j >> 1) & 3], v0), v1);
+                            b4[(j >> 1) & 3] = fminf(fminf(b4[(j >> 1) & 3], v0), v1);
+                        }
+                        mx = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));
+                        mn = fminf(fminf(b4[0], b4[1]), fminf(b4[2], b4[3]));
+                    } else {
+                        uint32_t r[32];
+                        tc_ld32(taddr, r);
+                        float a4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, b4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]);
+                            a4[j & 3] = fmaxf(a4[j & 3], j < k ? v : -INFINITY);
+                            b4[j & 3] = fminf(b4[j & 3], j < k ? v : INFINITY);
+                        }
+                        mx = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));
+                        mn = fminf(fminf(b4[0], b4[1]), fminf(b4[2], b4[3]));
                     }
-                    const float best = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3]));
-                    if (ch_ok) P.x2[pt * P.ld2 + ch] = best;
+                    float v = fmaf(s2, s2 >= 0.f ? mx : mn, t2);
+                    v = fmaxf(v, v * P.neg_slope);
+                    if (ch_ok) P.x2[pt * P.ld2 + ch] = v;
                 }
             }
             tc_fence_before();
@@ -221,7 +259,7 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == DG_MMA_WARP) {
+    if (warp == DG_ALLOC_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }

@@ -38,7 +38,8 @@ __device__ __forceinline__ int cell_coord(float v, float mn, float invh, int G) 
 
 __global__ void __launch_bounds__(GRID_BUILD_THREADS)
 knn_grid_build_kernel(const float* __restrict__ x, int N, int G, float4* __restrict__ sorted, int* __restrict__ sidx,
-                      int* __restrict__ cell_start, GridHeader* __restrict__ hdr) {
+                      int* __restrict__ cell_start, GridHeader* __restrict__ hdr,
+                      int* __restrict__ perm_out, int* __restrict__ inv_out, float* __restrict__ xyz_out) {
     __shared__ float red[7][32];
     __shared__ GridHeader h;
     __shared__ int counts[GRID_MAX_G * GRID_MAX_G * GRID_MAX_G + 1];
@@ -119,15 +120,40 @@ knn_grid_build_kernel(const float* __restrict__ x, int N, int G, float4* __restr
     int* cs = cell_start + (size_t)b * (GRID_MAX_G * GRID_MAX_G * GRID_MAX_G + 1);
     for (int i = tid; i <= cells; i += GRID_BUILD_THREADS) cs[i] = counts[i];
     __syncthreads();
-    // scatter (order inside a cell is arbitrary: the search result does not depend on it)
+    // stable scatter: inside a cell the points keep their original index order, so the cell order of a cloud is a pure
+    // function of the cloud (deterministic, batch-invariant).  Rounds of 1024 points; inside a round the 32 warps reserve
+    // their slots one after the other, lanes of a warp rank themselves among their same-cell peers with match.any.
     float4* so = sorted + (size_t)b * N;
     int* si = sidx + (size_t)b * N;
-    for (int i = tid; i < N; i += GRID_BUILD_THREADS) {
-        const float a = xb[i * 3], c = xb[i * 3 + 1], d = xb[i * 3 + 2];
-        const int cx = cell_coord(a, h.minx, h.invhx, G), cy = cell_coord(c, h.miny, h.invhy, G), cz = cell_coord(d, h.minz, h.invhz, G);
-        const int pos = atomicAdd(&counts[(cz * G + cy) * G + cx], 1);
-        so[pos] = make_float4(a, c, d, __fmaf_rn(d, d, __fmaf_rn(c, c, __fmaf_rn(a, a, 0.f))));
-        si[pos] = i;
+    for (int base = 0; base < N; base += GRID_BUILD_THREADS) {
+        const int i = base + tid;
+        const bool valid = i < N;
+        float a = 0.f, c = 0.f, d = 0.f;
+        int cell = cells;                                  // invalid lanes share a dummy cell
+        if (valid) {
+            a = xb[i * 3]; c = xb[i * 3 + 1]; d = xb[i * 3 + 2];
+            cell = (cell_coord(d, h.minz, h.invhz, G) * G + cell_coord(c, h.miny, h.invhy, G)) * G + cell_coord(a, h.minx, h.invhx, G);
+        }
+        const unsigned peers = __match_any_sync(kFull, cell);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        int slot = 0;
+        for (int w = 0; w < GRID_BUILD_THREADS / 32; ++w) {
+            if (warp == w && valid && lane == leader) {
+                slot = counts[cell];
+                counts[cell] = slot + __popc(peers);
+            }
+            __syncthreads();
+        }
+        slot = __shfl_sync(kFull, slot, leader);
+        if (valid) {
+            const int pos = slot + rank;
+            so[pos] = make_float4(a, c, d, __fmaf_rn(d, d, __fmaf_rn(c, c, __fmaf_rn(a, a, 0.f))));
+            si[pos] = i;
+            if (perm_out) perm_out[(size_t)b * N + pos] = i;
+            if (inv_out) inv_out[(size_t)b * N + i] = pos;
+            if (xyz_out) { float* o = xyz_out + ((size_t)b * N + pos) * 3; o[0] = a; o[1] = c; o[2] = d; }
+        }
     }
 }
 
@@ -257,7 +283,7 @@ extern "C" int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int i
     hdr = reinterpret_cast<GridHeader*>((reinterpret_cast<uintptr_t>(hdr) + 15) & ~(uintptr_t)15);
     const int G = grid_cells_per_axis(N);
     cudaStream_t st = as_stream(stream);
-    knn_grid_build_kernel<<<B, GRID_BUILD_THREADS, 0, st>>>(x, N, G, sorted, sidx, cell_start, hdr);
+    knn_grid_build_kernel<<<B, GRID_BUILD_THREADS, 0, st>>>(x, N, G, sorted, sidx, cell_start, hdr, nullptr, nullptr, nullptr);
     LPD_LAUNCH_CHECK();
     dim3 grid(ceil_div(N, GRID_Q_THREADS), B);
     const int gs = (k + 3) / 4;
@@ -271,6 +297,27 @@ extern "C" int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int i
         case 7: knn_grid_search_kernel<7><<<grid, GRID_Q_THREADS, 0, st>>>(sorted, sidx, cell_start, hdr, N, k, idx, idx_i64); break;
         default: knn_grid_search_kernel<8><<<grid, GRID_Q_THREADS, 0, st>>>(sorted, sidx, cell_start, hdr, N, k, idx, idx_i64); break;
     }
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+// Spatial (grid-cell) order of every cloud: perm[b][t] = original index of the t-th point in cell order (stable inside a
+// cell), inv = its inverse, xyz_sorted = the coordinates in that order.  The hot path is permutation-equivariant per point
+// and NetVLAD sums over the points, so the host modules may run a cloud in this order: neighbours in space become
+// neighbours in memory (gather locality) and the kNN candidate lists converge after the first few tiles.
+extern "C" int lpd_cell_order(const float* x, int B, int N, int32_t* perm, int32_t* inv, float* xyz_sorted,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    LPD_REQUIRE(x && perm && workspace && B >= 1 && B <= 65535 && N >= 1);
+    LPD_REQUIRE(((uintptr_t)workspace & 15) == 0);
+    if (workspace_bytes < lpd_knn_xyz_workspace_bytes(B, N)) return LPD_EWORKSPACE;
+    const size_t cells1 = GRID_MAX_G * GRID_MAX_G * GRID_MAX_G + 1;
+    float4* sorted = reinterpret_cast<float4*>(workspace);
+    int* sidx = reinterpret_cast<int*>(sorted + (size_t)B * N);
+    int* cell_start = sidx + (size_t)B * N;
+    GridHeader* hdr = reinterpret_cast<GridHeader*>(cell_start + (size_t)B * cells1);
+    hdr = reinterpret_cast<GridHeader*>((reinterpret_cast<uintptr_t>(hdr) + 15) & ~(uintptr_t)15);
+    knn_grid_build_kernel<<<B, GRID_BUILD_THREADS, 0, as_stream(stream)>>>(x, N, grid_cells_per_axis(N), sorted, sidx, cell_start, hdr,
+                                                                        perm, inv, xyz_sorted);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }

@@ -47,6 +47,18 @@ struct KnnTcParams {
     int qtiles, ctiles;    // per cloud
 };
 
+// Candidate tiles are streamed nearest-first in INDEX space around the query tile: 0, +1, -1, +2, -2, ... (mod ctiles, every
+// tile exactly once).  The host modules feed clouds in spatial (grid-cell) order, so index-near candidates are space-near
+// and, the features being smooth in space, feature-near: the lists' thresholds are almost final after the first few tiles
+// and later candidates fail the cheap threshold test.  (Streaming from tile 0 instead is the WORST case for a cloud in
+// spatial order: candidates improve monotonically and every one of them is inserted.)
+__device__ __forceinline__ int ct_of(int s, int center, int ctiles) {
+    const int d = (s + 1) >> 1;
+    int ct = center + ((s & 1) ? d : -d);
+    ct %= ctiles;
+    return ct < 0 ? ct + ctiles : ct;
+}
+
 __device__ __forceinline__ float to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -149,7 +161,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                 mbar_expect_tx(afull, S::A_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(a_s + kb * S::A_KB, &tmap_a, afull, kb * 32, b * P.N + q0);
-                for (int ct = 0; ct < P.ctiles; ++ct, ++tcount) {
+                for (int cs = 0; cs < P.ctiles; ++cs, ++tcount) {
+                    const int ct = ct_of(cs, q0 / KT_C, P.ctiles);
                     const uint32_t s = tcount % KT_BSTAGES, ph = (tcount / KT_BSTAGES) & 1;
                     mbar_wait_sleep(&bempty[s], ph ^ 1);
                     mbar_expect_tx(&bfull[s], S::B_BYTES + KT_C * 4);
@@ -209,7 +222,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int b = item / P.qtiles, q0 = (item % P.qtiles) * KT_Q;
             sel.reset();
-            for (int ct = 0; ct < P.ctiles; ++ct, ++tcount) {
+            for (int cs = 0; cs < P.ctiles; ++cs, ++tcount) {
+                const int ct = ct_of(cs, q0 / KT_C, P.ctiles);
                 const uint32_t ts = tcount % KT_TSTAGES, tph = (tcount / KT_TSTAGES) & 1;
                 mbar_wait(&tfull[ts], tph);
                 tc_fence_after();

@@ -116,6 +116,26 @@ def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
     return idx
 
 
+# Run each cloud in spatial (grid-cell) order inside the models (see lpd_cell_order): same descriptors up to fp32 summation
+# order, better gather locality and far fewer kNN list updates.
+SPATIAL_ORDER = True
+
+
+def cell_order(xyz: torch.Tensor, want_inv: bool = False):
+    """xyz [B, N, 3] -> (perm int32 [B, N], inv int32 [B, N] or None, xyz_sorted [B, N, 3])"""
+    lib = _lib.load()
+    xyz = _f32(xyz, "xyz").contiguous()
+    B, N, _ = xyz.shape
+    perm = torch.empty(B, N, device=xyz.device, dtype=torch.int32)
+    inv = torch.empty(B, N, device=xyz.device, dtype=torch.int32) if want_inv else None
+    out = torch.empty_like(xyz)
+    nbytes = lib.lpd_knn_xyz_workspace_bytes(B, N)
+    ws = torch.empty((nbytes + 3) // 4, device=xyz.device, dtype=torch.float32)
+    _call("lpd_cell_order", 1, lib.lpd_cell_order, xyz.data_ptr(), B, N, perm.data_ptr(), _p(inv), out.data_ptr(), ws.data_ptr(),
+          ws.numel() * 4, _stream())
+    return perm, inv, out
+
+
 def gemm(A, B, *, a_layout=A_MK, b_layout=B_NK, M, N, K, lda=None, ldb=None, out=None, ldc=None,
          batch=1, strideA=0, strideB=0, strideC=0, scale=None, shift=None, act=ACT_NONE, slope=0.0, aux=None):
     """out[b][m][n] = act(scale[n] * sum_k A[b][m][k] B[b][k][n] + shift[n]); see lpd_gemm."""

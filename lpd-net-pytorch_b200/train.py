@@ -139,6 +139,10 @@ class LPDNetTrain:
         self.act, self.slope = act, slope
         dev = x.device
         rows = x.detach().reshape(M, D).contiguous()
+        if ops.SPATIAL_ORDER and N >= 64:
+            # grid-cell order per cloud: every stage below is per-point equivariant, NetVLAD and the BatchNorm statistics
+            # sum over the points, and no input gradient is needed, so the parameter gradients are unchanged
+            rows = ops.cell_order(rows.view(B, N, 3))[2].view(M, 3)
         xyz = rows.view(B, N, 3)
         # conv1 / conv2 (+BN+act): always strict fp32 — they feed the feature-space kNN (see _LPDBase._front)
         self.l1, self.b1, self.l2, self.b2 = Linear(), BNAct(), Linear(), BNAct()

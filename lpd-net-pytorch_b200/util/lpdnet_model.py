@@ -77,13 +77,18 @@ def _act_code(module) -> tuple:
     return (ops.ACT_RELU, 0.0) if isinstance(module.act_f, nn.ReLU) else (ops.ACT_LEAKY, module.negative_slope)
 
 
-def _split_input(x: torch.Tensor, use_mFea: bool, who: str):
-    """[B,1,N,D] -> (point-major rows [B*N, D] contiguous, xyz [B,N,3] contiguous, B, N, D)"""
+def _split_input(x: torch.Tensor, use_mFea: bool, who: str, spatial_order: bool = False):
+    """[B,1,N,D] -> (point-major rows [B*N, D] contiguous, xyz [B,N,3] contiguous, B, N, D).
+    spatial_order: the points of every cloud are re-ordered into grid-cell order first (ops.cell_order); valid whenever the
+    caller consumes the per-point result through a permutation-invariant reduction (NetVLAD)."""
     require_cuda(x, who)
     if x.dim() != 4 or x.size(1) != 1:
         raise ValueError(f"{who}: expected input [B, 1, N, dims], got {tuple(x.shape)}")
     B, _, N, D = x.shape
     rows = x.detach().reshape(B * N, D).contiguous()
+    if spatial_order and D == 3 and N >= 64:
+        _, _, xs = ops.cell_order(rows.view(B, N, 3))
+        rows = xs.view(B * N, 3)
     if D > 3 or use_mFea:
         if D != 8:
             raise ValueError(f"{who}: use_mFea expects 8 input dims (xyz + 5 features), got {D}")
@@ -155,13 +160,13 @@ class TranformNet(nn.Module):
 class _LPDBase(nn.Module):
     """Common forward plumbing of LPDNet / LPDNetOrign."""
 
-    def _front(self, x, p, who):
+    def _front(self, x, p, who, spatial_order=False):
         """input split, optional T-Nets, conv1/conv2 -> (h2 [M,64], xyz_init [B,N,3], B, N).
         Everything here feeds the feature-space kNN, so it always runs in strict fp32 arithmetic (a TF32-rounded
         feature would move points across the k-th-neighbour boundary far beyond the few-ulp near-ties)."""
         prev = ops.set_precision("fp32")
         try:
-            rows, xyz_init, B, N, D = _split_input(x, self.use_mFea, who)
+            rows, xyz_init, B, N, D = _split_input(x, self.use_mFea, who, spatial_order)
             M = B * N
             act, slope = _act_code(self)
             if self.t3d:
@@ -178,7 +183,7 @@ class _LPDBase(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """[B, 1, N, dims] -> [B, emb_dims, N, 1] (reference layout)."""
-        f, B, N = self.forward_pm(x)
+        f, B, N = self.forward_pm(x, keep_order=True)
         return ops.transpose(f.view(B, N, self.emb_dims)).unsqueeze(-1)
 
 
@@ -227,12 +232,13 @@ class LPDNet(_LPDBase):
         p["ssn1"], p["tsn1"] = fold_bn(self.convSN1[1])
         return p
 
-    def forward_pm(self, x: torch.Tensor):
-        """-> (F [B*N, emb] point-major, B, N)"""
+    def forward_pm(self, x: torch.Tensor, keep_order: bool = False):
+        """-> (F [B*N, emb] point-major, B, N).  Unless keep_order, the rows of every cloud are in spatial (grid-cell)
+        order (ops.SPATIAL_ORDER): PointNetVlad feeds them to NetVLAD, which sums over the points."""
         require_cuda(x, "LPDNet")
         training_unsupported(self, "LPDNet")
         p = self._prep.get(self, self._build)
-        h, xyz_init, B, N = self._front(x, p, "LPDNet")
+        h, xyz_init, B, N = self._front(x, p, "LPDNet", ops.SPATIAL_ORDER and not keep_order)
         M, k = B * N, self.k
         act, slope = _act_code(self)
         dev = h.device
@@ -301,11 +307,11 @@ class LPDNetOrign(_LPDBase):
         p["ssn2"], p["tsn2"] = fold_bn(self.convSN2[1])
         return p
 
-    def forward_pm(self, x: torch.Tensor):
+    def forward_pm(self, x: torch.Tensor, keep_order: bool = False):
         require_cuda(x, "LPDNetOrign")
         training_unsupported(self, "LPDNetOrign")
         p = self._prep.get(self, self._build)
-        h, xyz_init, B, N = self._front(x, p, "LPDNetOrign")
+        h, xyz_init, B, N = self._front(x, p, "LPDNetOrign", ops.SPATIAL_ORDER and not keep_order)
         M, k = B * N, self.k
         act, slope = _act_code(self)
         dev = h.device

@@ -222,3 +222,26 @@ def test_run_model_tuple_layout(cuda, golden):
     with torch.no_grad():
         flat = model(x.view(6, 1, 1024, 3).cuda())
     assert torch.equal(torch.cat((o_q, o_p, o_o), 1).reshape(6, 256), flat)
+
+
+def test_spatial_order_is_a_deterministic_permutation_and_leaves_descriptors_unchanged(cuda, golden):
+    x = synth.clouds(3, 2048, seed=5)[:, 0].contiguous().cuda()
+    perm, inv, xs = ops.cell_order(x, want_inv=True)
+    perm2, _, _ = ops.cell_order(x)
+    assert torch.equal(perm, perm2)                                               # stable counting sort: no atomics order
+    p = perm.long()
+    assert torch.equal(torch.sort(p, 1)[0], torch.arange(2048, device="cuda").expand(3, -1))
+    assert torch.equal(torch.gather(x, 1, p.unsqueeze(-1).expand(-1, -1, 3)), xs)
+    assert torch.equal(torch.gather(inv.long(), 1, p), torch.arange(2048, device="cuda").expand(3, -1))
+    g = golden("c2_lpdnet_eval_small")
+    model, _ = build(g, num_points=1024, emb_dims=1024, featnet="lpdnet")
+    xin = synth.clouds(2, 1024).cuda()
+    with torch.no_grad():
+        on = model(xin)
+        prev, ops.SPATIAL_ORDER = ops.SPATIAL_ORDER, False
+        try:
+            off = model(xin)
+        finally:
+            ops.SPATIAL_ORDER = prev
+    assert (on - off).abs().max().item() <= 2e-6                                  # only the fp32 summation order differs
+    assert np.abs(on.cpu().numpy() - g["out"]).max() <= DESC_TOL
