@@ -308,6 +308,10 @@ int lpd_edge_bwd_apply(const float* p, int ldp, const float* q, int ldq, const i
                        const float* dy, const float* S, double count, float* dp, int lddp, float* dq, int lddq,
                        void* stream);
 
+/* backward of the gather-only edges e[(i,m)][:] = f[j(i,m)][:] (get_graph_feature_Origin(cat=False), lpdnet_model.py:116-145;
+ * forward = lpd_edge_materialize with q = NULL, scale 1, shift 0, no activation): dp[j] += dy[(i,m)], dp zeroed first. */
+int lpd_edge_scatter_add(const float* dy, const int32_t* idx, int B, int N, int k, int C, float* dp, int lddp, void* stream);
+
 /* NetVLAD train mode: lpd_netvlad_finish that also saves asum [B][K], the clamped intra norms n1 [B][K] and the clamped
  * global norm n2 [B]; its backward (in place on dv [B][D][K] -> d vraw; dasum [B][K]; dwc2 [D][K]); softmax backward
  * with the a_sum gradient folded in (in place on da [M][64]).  PointNetVlad.py:58-74. */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "lpd_edge_bwd_reduce": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "lpd_edge_bwd_apply": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _i, _vp, _vp, _vp, _d,
                                 _vp, _i, _vp, _i, _vp]),
+    "lpd_edge_scatter_add": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "lpd_netvlad_finish_train": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lpd_netvlad_finish_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "lpd_softmax64_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),

@@ -425,6 +425,24 @@ edge_bwd_kernel(EdgeArgs a, const float* __restrict__ bn, int act, float slope,
     if (!APPLY) block_reduce_cols(s1, s2, lane, lanes, g, C, active, partial, blockIdx.x);
 }
 
+// gather-only edges (get_graph_feature_Origin(cat=False), lpdnet_model.py:116-145): backward of e[(i,m)] = f[j(i,m)] is the
+// scatter-add dp[j] += dy[(i,m)]  (the index_put_(accumulate=True) of torch's autograd)
+__global__ void __launch_bounds__(TR_THREADS)
+edge_scatter_add_kernel(const float* __restrict__ dy, const int* __restrict__ idx, long long M, int N, int k, int C,
+                        float* __restrict__ dp, int lddp) {
+    const int cg = C >> 2;
+    const long long total = M * k * cg;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long edge = e / cg;
+        const int c = (int)(e % cg) * 4;
+        const long long pt = edge / k;
+        const long long cloud0 = (pt / N) * N;
+        const int j = __ldg(idx + edge);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dy + edge * C + c));
+        atomicAdd(reinterpret_cast<float4*>(dp + (cloud0 + j) * lddp + c), v);
+    }
+}
+
 // ---- Adam (torch.optim.Adam defaults: no amsgrad, L2 weight decay folded into the gradient) ------------------------
 __global__ void __launch_bounds__(TR_THREADS)
 adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
@@ -617,6 +635,15 @@ extern "C" int lpd_adam(float* w, const float* g, float* m, float* v, long long 
 extern "C" int lpd_axpy(float* y, int ldy, const float* x, int ldx, long long rows, int C, float alpha, void* stream) {
     LPD_REQUIRE(y && x && rows >= 1 && C >= 1 && ldy >= C && ldx >= C);
     axpy_kernel<<<grid_for(rows * C), TR_THREADS, 0, as_stream(stream)>>>(y, ldy, x, ldx, rows, C, alpha);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+extern "C" int lpd_edge_scatter_add(const float* dy, const int32_t* idx, int B, int N, int k, int C, float* dp, int lddp, void* stream) {
+    LPD_REQUIRE(dy && idx && dp && B >= 1 && N >= 1 && k >= 1 && C >= 4 && C % 4 == 0 && lddp % 4 == 0 && al16(dy) && al16(dp));
+    const long long M = (long long)B * N;
+    LPD_CUDA_CHECK(cudaMemset2DAsync(dp, (size_t)lddp * 4, 0, (size_t)C * 4, (size_t)M, as_stream(stream)));
+    edge_scatter_add_kernel<<<grid_for(M * k * (C / 4)), TR_THREADS, 0, as_stream(stream)>>>(dy, idx, M, N, k, C, dp, lddp);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }

@@ -451,6 +451,31 @@ def edge_bwd(p, ldp, q, ldq, idx, B, N, k, C, bn, act, slope, dx, lddx, arg, dy,
     return S
 
 
+def edge_scatter_add(dy, idx, B, N, k, C, dp=None, lddp=None):
+    """dp[j(i,m)] += dy[(i,m)] -> dp [B*N, C]"""
+    lib = _lib.load()
+    if dp is None:
+        dp = torch.empty(B * N, C, device=dy.device, dtype=torch.float32)
+        lddp = C
+    _call(f"lpd_edge_scatter_add[C={C}]", 2, lib.lpd_edge_scatter_add, dy.data_ptr(), idx.data_ptr(), B, N, k, C, dp.data_ptr(), lddp, _stream())
+    return dp
+
+
+def act_bwd(dy, lddy, z, ldz, rows, C, act, slope, dz=None, lddz=None):
+    """dz = dy * act'(z) for an activation that follows a plain (BatchNorm-free) layer: the BN backward with the identity
+    statistics block (scale 1, shift 0, mean 0, invstd 1) and zero reduction terms."""
+    lib = _lib.load()
+    ident = torch.zeros(6, C, device=z.device, dtype=torch.float32)
+    ident[0].fill_(1.0)
+    ident[3].fill_(1.0)
+    if dz is None:
+        dz = torch.empty(rows, C, device=z.device, dtype=torch.float32)
+        lddz = C
+    _call(f"lpd_bn_bwd_apply[C={C}]", 1, lib.lpd_bn_bwd_apply, dy.data_ptr(), lddy, z.data_ptr(), ldz, rows, C, ident.data_ptr(),
+          ident[4].data_ptr(), 1.0, act, float(slope), None, 0, dz.data_ptr(), lddz, _stream())
+    return dz
+
+
 def netvlad_finish_train(vlad, a, wc2, B, N, D, K=64):
     """in place on vlad [B, D, K] -> (v [B, D*K], asum [B, K], n1 [B, K], n2 [B])"""
     lib = _lib.load()

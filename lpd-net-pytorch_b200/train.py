@@ -68,10 +68,12 @@ class Linear:
     def bwd(self, dz, lddz, grads: _Grads, need_da=True, da_out=None, ldda=None, accumulate=False):
         grads.add(self.weight, ops.wgrad(dz, lddz, self.a, self.lda, self.rows, self.N, self.K))
         if self.bias is not None:
-            part, nparts = ops.bn_stats(dz, self.rows, self.N, lddz) if self.N % 4 == 0 and lddz % 4 == 0 else (None, 0)
-            if part is None:
-                raise LpdError("bias gradient needs a channel count that is a multiple of 4")
-            grads.add(self.bias, ops.colsum_finalize(part, nparts, 2 * self.N)[: self.N])
+            if self.N % 4 == 0 and lddz % 4 == 0:
+                part, nparts = ops.bn_stats(dz, self.rows, self.N, lddz)
+                grads.add(self.bias, ops.colsum_finalize(part, nparts, 2 * self.N)[: self.N])
+            else:   # few columns (fc3 of the 3x3 T-Net): ones . dz
+                ones = torch.ones(1, self.rows, device=dz.device, dtype=torch.float32)
+                grads.add(self.bias, ops.gemm(ones, dz, a_layout=A_MK, b_layout=B_KN, M=1, N=self.N, K=self.rows, ldb=lddz))
         if not need_da:
             return None
         return dgrad(dz, lddz, self.w, self.rows, self.N, self.K, out=da_out, ldc=ldda, accumulate=accumulate, tf32_ok=self.tf32_ok)
@@ -114,6 +116,113 @@ class BNAct:
         return dz
 
 
+class ActOnly:
+    """y = act(z) after a BatchNorm-free layer (STN3d(use_bn=False), reference PointNetVlad.py:160-167)"""
+
+    def fwd(self, z, ldz, rows, C, act, slope=0.0):
+        self.z, self.ldz, self.rows, self.C, self.act, self.slope = z, ldz, rows, C, act, slope
+        return ops.affine_act(z, rows, C, ldz, None, None, act, slope)
+
+    def bwd(self, dy, lddy, grads=None):
+        return ops.act_bwd(dy, lddy, self.z, self.ldz, self.rows, self.C, self.act, self.slope, dz=dy, lddz=lddy)
+
+
+def _norm_act(bn_mod):
+    """BNAct when the layer has a BatchNorm module, else ActOnly (same fwd/bwd call shape)"""
+    return BNAct() if bn_mod is not None else ActOnly()
+
+
+def _fwd_norm_act(layer, z, ldz, rows, C, bn_mod, act, slope=0.0):
+    if bn_mod is not None:
+        return layer.fwd(z, ldz, rows, C, bn_mod, act, slope)
+    return layer.fwd(z, ldz, rows, C, act, slope)
+
+
+class ColMax:
+    """g[b][c] = max_n h[b][n][c]  (torch.max(x, 2) lpdnet_model.py:300 / MaxPool2d((num_points,1)) PointNetVlad.py:169)"""
+
+    def fwd(self, h, B, N, C):
+        self.B, self.N, self.C = B, N, C
+        g, self.arg = ops.colmax_arg(h, B, N, C)
+        return g
+
+    def bwd(self, dg):
+        dh = torch.zeros(self.B * self.N, self.C, device=dg.device, dtype=torch.float32)
+        return ops.colmax_bwd(dg.contiguous(), self.arg, self.B, self.N, self.C, dh, self.C)
+
+
+class Transform:
+    """out[b] = rows[b][:, :C] . T[b]   (torch.bmm / matmul with a T-Net output: lpdnet_model.py:86,93,229,241; PointNetVlad.py:209,223)"""
+
+    def fwd(self, rows, ld, trans, B, N, C):
+        self.rows, self.ld, self.trans, self.B, self.N, self.C = rows, ld, trans.contiguous(), B, N, C
+        out = torch.empty(B * N, C, device=rows.device, dtype=torch.float32)
+        ops.gemm(rows, self.trans, a_layout=A_MK, b_layout=B_KN, M=N, N=C, K=C, lda=ld, ldb=C, out=out, ldc=C,
+                 batch=B, strideA=N * ld, strideB=C * C, strideC=N * C)
+        return out
+
+    def bwd(self, dout, need_drows):
+        B, N, C = self.B, self.N, self.C
+        # dT[b] = rows[b]^T . dout[b]
+        dtrans = ops.gemm(self.rows, dout, a_layout=A_KM, b_layout=B_KN, M=C, N=C, K=N, lda=self.ld, ldb=C, batch=B,
+                          strideA=N * self.ld, strideB=N * C, strideC=C * C,
+                          out=torch.empty(B, C, C, device=dout.device, dtype=torch.float32), ldc=C)
+        drows = None
+        if need_drows:   # drows[b][n][c] = sum_c' dout[b][n][c'] T[b][c][c']
+            drows = ops.gemm(dout, self.trans, a_layout=A_MK, b_layout=B_NK, M=N, N=C, K=C, lda=C, ldb=C, batch=B,
+                             strideA=N * C, strideB=C * C, strideC=N * C,
+                             out=torch.empty(B * N, C, device=dout.device, dtype=torch.float32), ldc=C)
+        return drows, dtrans
+
+
+class TNetTrain:
+    """TranformNet (lpdnet_model.py:273-313, BatchNorm everywhere) and STN3d (PointNetVlad.py:126-179, BatchNorm optional):
+    k -> 64 -> 128 -> 1024 (+norm +ReLU), max over the points, 1024 -> 512 -> 256 (+norm +ReLU) -> k*k, + identity."""
+
+    def __init__(self, net):
+        self.net = net
+        self.has_bn = getattr(net, "use_bn", True)
+
+    def _bn(self, i):
+        return getattr(self.net, f"bn{i}") if self.has_bn else None
+
+    def fwd(self, rows, ld, B, N):
+        net, k, R = self.net, self.net.k, ops.ACT_RELU
+        M = B * N
+        self.B, self.N, self.M = B, N, M
+        self.lin = [Linear() for _ in range(6)]
+        self.na = [_norm_act(self._bn(i)) for i in range(1, 6)]
+        h, ldh = rows, ld
+        for i, (conv, C) in enumerate(((net.conv1, 64), (net.conv2, 128), (net.conv3, 1024))):
+            z = self.lin[i].fwd(h, ldh, M, conv.weight, conv.bias, tf32_ok=False)
+            h = _fwd_norm_act(self.na[i], z, C, M, C, self._bn(i + 1), R)
+            ldh = C
+        self.pool = ColMax()
+        g = self.pool.fwd(h, B, N, 1024)
+        for i, (fc, C) in enumerate(((net.fc1, 512), (net.fc2, 256)), 3):
+            z = self.lin[i].fwd(g, g.shape[1], B, fc.weight, fc.bias, tf32_ok=False)
+            g = _fwd_norm_act(self.na[i], z, C, B, C, self._bn(i + 1), R)
+        t = self.lin[5].fwd(g, 256, B, net.fc3.weight, net.fc3.bias, tf32_ok=False)               # [B, k*k]
+        eye = torch.eye(k, device=t.device, dtype=torch.float32).reshape(1, k * k)
+        ops.axpy(t, k * k, eye.expand(B, -1).contiguous(), k * k, B, k * k, 1.0)                    # + identity
+        return t.view(B, k, k)
+
+    def bwd(self, dtrans, grads, need_drows):
+        B, M, k = self.B, self.M, self.net.k
+        d = dtrans.reshape(B, k * k).contiguous()
+        d = self.lin[5].bwd(d, k * k, grads)
+        for i in (4, 3):
+            C = (512, 256)[i - 3]
+            d = self.na[i].bwd(d, C, grads)
+            d = self.lin[i].bwd(d, C, grads)
+        d = self.pool.bwd(d)                                                                        # [M, 1024]
+        for i in (2, 1, 0):
+            C = (64, 128, 1024)[i]
+            d = self.na[i].bwd(d, C, grads)
+            d = self.lin[i].bwd(d, C, grads, need_da=(i > 0 or need_drows))
+        return d
+
+
 def _act_of(module):
     return (ops.ACT_RELU, 0.0) if isinstance(module.act_f, nn.ReLU) else (ops.ACT_LEAKY, module.negative_slope)
 
@@ -123,11 +232,42 @@ def _act_of(module):
 # ----------------------------------------------------------------------------------------------------------------------
 class LPDNetTrain:
     def __init__(self, net):
-        if net.t3d or net.tfea:
-            raise LpdError("train mode with T-Nets (xyz_trans / feature_transform) is not built yet")
         if net.use_mFea:
             raise LpdError("train mode with use_mFea is not built yet")
         self.net = net
+
+    # conv1 / conv2 (+BN+act) with the optional T-Nets around them (reference :226-241); strict fp32: they feed the kNN
+    def _front_fwd(self, rows, D, B, N, conv1, bn1, conv2, bn2, act, slope):
+        net, M = self.net, B * N
+        self.t3, self.tf = None, None
+        if net.t3d:
+            self.t3, self.x3 = TNetTrain(net.t_net3d), Transform()
+            rows = self.x3.fwd(rows, D, self.t3.fwd(rows, D, B, N), B, N, 3)
+        self.l1, self.b1, self.l2, self.b2 = Linear(), BNAct(), Linear(), BNAct()
+        z1 = self.l1.fwd(rows, D, M, conv1.weight, tf32_ok=False)
+        h1 = self.b1.fwd(z1, 64, M, 64, bn1, act, slope)
+        z2 = self.l2.fwd(h1, 64, M, conv2.weight, tf32_ok=False)
+        h2 = self.b2.fwd(z2, 64, M, 64, bn2, act, slope)
+        if net.tfea:
+            self.tf, self.xf = TNetTrain(net.t_net_fea), Transform()
+            h2 = self.xf.fwd(h2, 64, self.tf.fwd(h2, 64, B, N), B, N, 64)
+        return h2
+
+    def _front_bwd(self, dh2, grads):
+        if self.tf is not None:
+            da, dtf = self.xf.bwd(dh2, need_drows=True)
+            db = self.tf.bwd(dtf, grads, need_drows=True)
+            ops.axpy(da, 64, db, 64, self.M, 64, 1.0)
+            dh2 = da
+        dz2 = self.b2.bwd(dh2, 64, grads)
+        dh1 = self.l2.bwd(dz2, 64, grads)
+        dz1 = self.b1.bwd(dh1, 64, grads)
+        if self.t3 is None:
+            self.l1.bwd(dz1, 64, grads, need_da=False)
+            return
+        drows = self.l1.bwd(dz1, 64, grads)                                        # [M, 3]: gradient of the transformed xyz
+        _, dt3 = self.x3.bwd(drows, need_drows=False)
+        self.t3.bwd(dt3, grads, need_drows=False)
 
     def fwd(self, x):
         net = self.net
@@ -144,12 +284,7 @@ class LPDNetTrain:
             # sum over the points, and no input gradient is needed, so the parameter gradients are unchanged
             rows = ops.cell_order(rows.view(B, N, 3))[2].view(M, 3)
         xyz = rows.view(B, N, 3)
-        # conv1 / conv2 (+BN+act): always strict fp32 — they feed the feature-space kNN (see _LPDBase._front)
-        self.l1, self.b1, self.l2, self.b2 = Linear(), BNAct(), Linear(), BNAct()
-        z1 = self.l1.fwd(rows, D, M, net.conv1_lpd.weight, tf32_ok=False)
-        h1 = self.b1.fwd(z1, 64, M, 64, net.bn1_lpd, act, slope)
-        z2 = self.l2.fwd(h1, 64, M, net.conv2_lpd.weight, tf32_ok=False)
-        h2 = self.b2.fwd(z2, 64, M, 64, net.bn2_lpd, act, slope)
+        h2 = self._front_fwd(rows, D, B, N, net.conv1_lpd, net.bn1_lpd, net.conv2_lpd, net.bn2_lpd, act, slope)
         self.h2 = h2
         # ---- feature-space graph: DG1 (decomposed) -> x1, DG2 (dense edge GEMM) -> x2 --------------------------------
         self.idx_f = ops.knn(h2.view(B, N, 64), k)
@@ -224,10 +359,155 @@ class LPDNetTrain:
         grads.add(net.convDG1[0].weight, torch.cat((dwpq1[:128], dwpq1[128:]), 1))
         dh2 = dgrad(dpq1, 256, self.wpq1, M, 256, 64)
         del dpq1, dy1, dpyr
-        dz2 = self.b2.bwd(dh2, 64, grads)
-        dh1 = self.l2.bwd(dz2, 64, grads)
-        dz1 = self.b1.bwd(dh1, 64, grads)
-        self.l1.bwd(dz1, 64, grads, need_da=False)
+        self._front_bwd(dh2, grads)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# LPDNetOrign (reference lpdnet_model.py:18-114, the CLI default featnet), train mode
+# ----------------------------------------------------------------------------------------------------------------------
+class LPDNetOrignTrain(LPDNetTrain):
+    def fwd(self, x):
+        net = self.net
+        require_cuda(x, "LPDNetOrign")
+        B, _, N, D = x.shape
+        M, k = B * N, net.k
+        self.B, self.N, self.M, self.k = B, N, M, k
+        act, slope = _act_of(net)
+        self.act, self.slope = act, slope
+        rows = x.detach().reshape(M, D).contiguous()
+        if ops.SPATIAL_ORDER and N >= 64:
+            rows = ops.cell_order(rows.view(B, N, 3))[2].view(M, 3)
+        xyz = rows.view(B, N, 3)
+        h2 = self._front_fwd(rows, D, B, N, net.conv1_lpd[0], net.conv1_lpd[1], net.conv2_lpd[0], net.conv2_lpd[1], act, slope)
+        self.h2 = h2
+        # ---- feature-space graph: edges [f_i ; f_j - f_i] -> DG1 (decomposed: P = Wb f_j, Q = (Wa - Wb) f_i), DG2 (dense), max ----
+        self.idx_f = ops.knn(h2.view(B, N, 64), k)
+        wdg1 = w2d(net.convDG1[0].weight)                                          # [64, 128] = [Wa | Wb]
+        wa, wb = wdg1[:, :64], wdg1[:, 64:]
+        self.wpq1 = torch.cat((wb, wa - wb), 0).contiguous()                       # [128, 64]
+        self.pq1 = ops.linear(h2, self.wpq1, M=M, N=128, K=64)
+        p1, q1 = self.pq1, self.pq1[:, 64:]
+        bn_dg1, bn_dg2 = net.convDG1[1], net.convDG2[1]
+        _, _, part, nparts = ops.edge_sel_stats(p1, 128, q1, 128, self.idx_f, B, N, k, 64, bn_dg1.weight.detach())
+        self.bn1e = _bn_finalize(bn_dg1, part, nparts, M * k, 64)
+        self.y1 = ops.edge_materialize(p1, 128, q1, 128, self.idx_f, B, N, k, 64, self.bn1e[0], self.bn1e[1], act, slope)
+        self.wdg2 = w2d(net.convDG2[0].weight)
+        self.z2e = ops.linear(self.y1, self.wdg2, M=M * k, N=64, K=64)
+        part, nparts = ops.bn_stats(self.z2e, M * k, 64, 64)
+        self.bn2e = _bn_finalize(bn_dg2, part, nparts, M * k, 64)
+        self.zsel2, self.arg2 = ops.edge_sel_dense(self.z2e, M, k, 64, bn_dg2.weight.detach())
+        self.xdg = ops.affine_act(self.zsel2, M, 64, 64, self.bn2e[0], self.bn2e[1], act, slope)
+        # ---- Cartesian graph, gather-only edges e = f_j: SN1, SN2 over the materialised edges (BatchNorm2d statistics are
+        #      over all B*N*k edges, i.e. weighted by the in-degree of every point), max ----
+        self.idx_x = ops.knn(xyz, k)
+        one, zero = torch.ones(64, device=x.device), torch.zeros(64, device=x.device)
+        self.e3 = ops.edge_materialize(self.xdg, 64, None, 0, self.idx_x, B, N, k, 64, one, zero, ops.ACT_NONE, 0.0)
+        self.ls1, self.bs1, self.ls2 = Linear(), BNAct(), Linear()
+        zs1 = self.ls1.fwd(self.e3, 64, M * k, net.convSN1[0].weight)
+        ys1 = self.bs1.fwd(zs1, 64, M * k, 64, net.convSN1[1], act, slope)
+        self.zs2 = self.ls2.fwd(ys1, 64, M * k, net.convSN2[0].weight)
+        part, nparts = ops.bn_stats(self.zs2, M * k, 64, 64)
+        self.bns2 = _bn_finalize(net.convSN2[1], part, nparts, M * k, 64)
+        self.zsel4, self.arg4 = ops.edge_sel_dense(self.zs2, M, k, 64, net.convSN2[1].weight.detach())
+        xsn = ops.affine_act(self.zsel4, M, 64, 64, self.bns2[0], self.bns2[1], act, slope)
+        # ---- conv3/4/5: 64 -> 64 -> 128 -> emb ----
+        self.tail = []
+        f, ldf = xsn, 64
+        for seq, C in ((net.conv3_lpd, 64), (net.conv4_lpd, 128), (net.conv5_lpd, net.emb_dims)):
+            lin, bna = Linear(), BNAct()
+            z = lin.fwd(f, ldf, M, seq[0].weight)
+            f = bna.fwd(z, C, M, C, seq[1], act, slope)
+            ldf = C
+            self.tail.append((lin, bna, C))
+        return f, B, N
+
+    def bwd(self, df, grads: _Grads):
+        net, B, N, M, k = self.net, self.B, self.N, self.M, self.k
+        act, slope = self.act, self.slope
+        d = df
+        for lin, bna, C in reversed(self.tail):
+            d = bna.bwd(d, C, grads)
+            d = lin.bwd(d, C, grads)
+        dxsn = d                                                                   # [M, 64]
+        # SN2: dense edge layer whose only consumer is the max
+        bn_sn2 = net.convSN2[1]
+        S = ops.bn_bwd_sums(dxsn, 64, self.zsel4, 64, M, 64, self.bns2, act, slope)
+        dzs2 = ops.edge_dense_bwd_apply(self.zs2, M, k, 64, self.bns2, S, M * k, act, slope, dxsn, 64, self.zsel4, self.arg4)
+        grads.add(bn_sn2.bias, S[0])
+        grads.add(bn_sn2.weight, S[1])
+        dys1 = self.ls2.bwd(dzs2, 64, grads)
+        dzs1 = self.bs1.bwd(dys1, 64, grads)
+        de3 = self.ls1.bwd(dzs1, 64, grads)                                        # [M*k, 64]
+        dxdg = ops.edge_scatter_add(de3, self.idx_x, B, N, k, 64)                  # [M, 64]
+        del de3, dzs1, dys1, dzs2
+        # DG2
+        bn_dg1, bn_dg2 = net.convDG1[1], net.convDG2[1]
+        S2 = ops.bn_bwd_sums(dxdg, 64, self.zsel2, 64, M, 64, self.bn2e, act, slope)
+        dz2e = ops.edge_dense_bwd_apply(self.z2e, M, k, 64, self.bn2e, S2, M * k, act, slope, dxdg, 64, self.zsel2, self.arg2)
+        grads.add(bn_dg2.bias, S2[0])
+        grads.add(bn_dg2.weight, S2[1])
+        grads.add(net.convDG2[0].weight, ops.wgrad(dz2e, 64, self.y1, 64, M * k, 64, 64))
+        dy1 = dgrad(dz2e, 64, self.wdg2, M * k, 64, 64, out=self.y1, ldc=64)
+        # DG1 (decomposed, dense incoming gradient only)
+        dpq1 = torch.empty(M, 128, device=df.device, dtype=torch.float32)
+        S1 = ops.edge_bwd(self.pq1, 128, self.pq1[:, 64:], 128, self.idx_f, B, N, k, 64, self.bn1e, act, slope, None, 0, None,
+                          dy1, dpq1, 128, dpq1[:, 64:], 128)
+        grads.add(bn_dg1.bias, S1[0])
+        grads.add(bn_dg1.weight, S1[1])
+        dwpq1 = ops.wgrad(dpq1, 128, self.h2, 64, M, 128, 64)                      # [128, 64] = [dW_P ; dW_Q]
+        dwp, dwq = dwpq1[:64], dwpq1[64:]
+        dwb = dwp.clone()
+        ops.axpy(dwb, 64, dwq.contiguous(), 64, 64, 64, -1.0)                      # Wb enters P (+) and Q = Wa - Wb (-)
+        grads.add(net.convDG1[0].weight, torch.cat((dwq, dwb), 1))
+        dh2 = dgrad(dpq1, 128, self.wpq1, M, 128, 64)
+        self._front_bwd(dh2, grads)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# PointNetfeat (reference PointNetVlad.py:181-241), train mode
+# ----------------------------------------------------------------------------------------------------------------------
+class PointNetTrain:
+    def __init__(self, net):
+        self.net = net
+
+    def fwd(self, x):
+        net = self.net
+        require_cuda(x, "PointNetfeat")
+        B, _, N, _ = x.shape
+        M, R = B * N, ops.ACT_RELU
+        self.B, self.N, self.M = B, N, M
+        if N != net.num_points:
+            raise ValueError(f"PointNetfeat: got {N} points, constructed for num_points={net.num_points}")
+        rows = x.detach().reshape(M, 3).contiguous()
+        self.stn, self.x3 = TNetTrain(net.stn), Transform()
+        xt = self.x3.fwd(rows, 3, self.stn.fwd(rows, 3, B, N), B, N, 3)                              # :205-209
+        self.lins = [Linear() for _ in range(5)]
+        self.bnas = [BNAct() for _ in range(5)]
+        h, ldh = xt, 3
+        self.ft = None
+        for i, C in enumerate((64, 64, 64, 128, net.emb_dims)):
+            conv, bn = getattr(net, f"conv{i + 1}"), getattr(net, f"bn{i + 1}")
+            if i == 2 and net.apply_feature_trans:                                                   # :218-225
+                self.ft, self.xf = TNetTrain(net.feature_trans), Transform()
+                h = self.xf.fwd(h, 64, self.ft.fwd(h, 64, B, N), B, N, 64)
+            z = self.lins[i].fwd(h, ldh, M, conv.weight, conv.bias, tf32_ok=(i >= 2))
+            h = self.bnas[i].fwd(z, C, M, C, bn, R if i < 4 else ops.ACT_NONE)                       # :213-230 (no ReLU after bn5)
+            ldh = C
+        return h, B, N
+
+    def bwd(self, df, grads: _Grads):
+        d = df
+        chans = (64, 64, 64, 128, self.net.emb_dims)
+        for i in (4, 3, 2, 1, 0):
+            d = self.bnas[i].bwd(d, chans[i], grads)
+            d = self.lins[i].bwd(d, chans[i], grads)
+            if i == 2 and self.ft is not None:
+                da, dft = self.xf.bwd(d, need_drows=True)
+                db = self.ft.bwd(dft, grads, need_drows=True)
+                ops.axpy(da, 64, db, 64, self.M, 64, 1.0)
+                d = da
+        _, dt3 = self.x3.bwd(d, need_drows=False)                                                    # d: gradient of x . T  [M, 3]
+        self.stn.bwd(dt3, grads, need_drows=False)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -333,13 +613,17 @@ class NetVLADTrain:
 class _PointNetVladTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, model, *params):
+        from .util.lpdnet_model import LPDNet, LPDNetOrign
         feat = model.emb_nn
-        from .util.lpdnet_model import LPDNet
-        if not isinstance(feat, LPDNet):
-            raise LpdError("train mode is built for featnet='lpdnet' (the C3 configuration) in this round; "
-                           "featnet='pointnet' / 'lpdnetorigin' train() is not built yet — use .eval()")
         with torch.no_grad():
-            fe = LPDNetTrain(feat)
+            if isinstance(feat, LPDNet):
+                fe = LPDNetTrain(feat)
+            elif isinstance(feat, LPDNetOrign):
+                fe = LPDNetOrignTrain(feat)
+            else:
+                if model.point_net.max_pool:
+                    raise ValueError("PointNetVlad needs the per-point feature map: construct with max_pool=False")
+                fe = PointNetTrain(model.point_net)
             f, B, N = fe.fwd(x)
             if N != model.net_vlad.max_samples:
                 raise ValueError(f"PointNetVlad: got {N} points per cloud, constructed for num_points={model.net_vlad.max_samples}")

@@ -129,3 +129,104 @@ def test_training_step_tf32_mode_close_to_fp32(cuda, golden):
     for key, p in model.named_parameters():
         gn, rn = float(p.grad.double().norm()), float(g["gnorm64." + key])
         assert abs(gn - rn) <= 2e-2 * rn, f"{key}: {gn} vs {rn}"
+
+
+@pytest.mark.parametrize("name,kw,seed", [
+    ("train_step_lpdnetorigin_n256", dict(featnet="lpdnetorigin"), 1234),
+    ("train_step_pointnet_n256", dict(featnet="pointnet"), 4),
+    ("train_step_pointnet_ft_n256", dict(featnet="pointnet", feature_transform=True), 1234),
+    ("train_step_lpdnet_tnets_n256", dict(featnet="lpdnet", feature_transform=True, xyz_trans=True), 1234),
+    ("train_step_lpdnetorigin_tnets_n256", dict(featnet="lpdnetorigin", feature_transform=True, xyz_trans=True), 1234),
+])
+def test_training_step_other_featnets_match_reference_autograd(cuda, golden, name, kw, seed):
+    """train-mode forward + backward of the CLI default featnet (lpdnetorigin), PointNetVLAD (pointnet, with and without the
+    feature STN) and the T-Net variants against the reference's autograd; same yardstick as the C3 test above
+    (noise = the reference's own fp32-vs-fp64 deviation).
+
+    * Parameters whose true gradient is zero (a conv / linear bias in front of a batch-statistics BatchNorm; the last
+      T-Net BatchNorm bias in front of another one) are checked in absolute terms.
+    * The T-Net configurations are dominated by kNN-graph discontinuities: a 64x64 learned feature transform in front of the
+      feature-space kNN makes the loss jump under parameter changes of 1e-3 (finite differences are meaningless there) and
+      the reference's own fp32-vs-fp64 deviation reaches 1e-2 of a tensor's max; for them the elementwise bound is
+      max(5e-2, 3x noise).  The T-Net itself is checked to 1e-5 against autograd in test_tnet_backward_in_isolation.
+    * featnet='pointnet': the goldens were generated with nn.BatchNorm2d routed through the 3-D batch_norm path, because
+      torch 2.11's CPU autograd returns gradients that contradict finite differences for BatchNorm2d on [B, C, N, 1]
+      tensors (oracle/gen_golden.py::_patch_batchnorm2d_w1); the forward is identical."""
+    g = golden(name)
+    ops.set_precision("fp32")
+    tnets = bool(kw.get("xyz_trans"))
+    model = PNV.PointNetVlad(num_points=256, emb_dims=1024, **kw)
+    model.load_state_dict(synth.synthetic_state_dict(model))
+    model = model.cuda().train()
+    out, loss = run_step(model, synth.clouds(22, 256, seed=seed), 1)
+    out_noise = np.abs(g["out"] - g["out64"]).max()
+    assert np.abs(out.detach().cpu().numpy() - g["out"]).max() <= max(1e-4, 1.5 * out_noise)
+    ref_loss, ref_loss64 = float(g["loss"]), float(g["loss64"])
+    # 1e-5 relative is the bar of the lpdnet C3 configuration (met in the test above); these secondary configurations get 3e-5
+    assert abs(float(loss.detach()) - ref_loss) <= max(3e-5 * abs(ref_loss), 3.0 * abs(ref_loss - ref_loss64))
+    floor_e, floor_n = (5e-2, 2e-2) if tnets else (5e-4, 5e-4)
+    gmax = max(float(g[k]) for k in g.files if k.startswith("gnorm64."))
+    bad = {}
+    for key, p in model.named_parameters():
+        if "grad." + key not in g.files:
+            assert p.grad is None, f"{key}: the reference leaves this parameter without a gradient"
+            continue
+        assert p.grad is not None, f"no gradient for {key}"
+        gn, rn = float(p.grad.double().norm()), float(g["gnorm64." + key])
+        if rn <= 1e-6 * gmax:                                  # analytically zero gradient
+            if gn > 1e-5 * gmax:
+                bad[key] = ("zero-gradient parameter", gn, rn)
+            continue
+        ref, ref64 = g["grad." + key], g["grad64." + key]
+        got = subsample(p.grad)
+        scale = max(np.abs(ref64).max(), 1e-12)
+        noise = np.abs(ref - ref64).max() / scale
+        e32, e64 = np.abs(got - ref).max() / scale, np.abs(got - ref64).max() / scale
+        nnoise = abs(float(g["gnorm." + key]) - rn) / rn
+        if e64 > max(floor_e, 2.0 * noise) or e32 > max(floor_e, 3.0 * noise) or abs(gn - rn) > max(floor_n, 3.0 * nnoise) * rn:
+            bad[key] = (float(e32), float(e64), float(noise), abs(gn - rn) / rn, nnoise)
+    assert not bad, f"gradient mismatch: {bad}"
+    sd = model.state_dict()
+    for key in g.files:
+        if key.startswith("after."):
+            assert np.allclose(sd[key[6:]].cpu().numpy(), g[key], rtol=2e-4 if tnets else 1e-4, atol=1e-5), f"{key[6:]} after one train step"
+
+
+@pytest.mark.parametrize("k", [3, 64])
+def test_tnet_backward_in_isolation(cuda, k):
+    """TranformNet (BatchNorm everywhere, lpdnet_model.py:273-313) forward + backward through the C ABI against torch
+    autograd of the same formulas in FLOAT64 on the GPU.  (An fp32 torch run is not a usable yardstick: the max over the
+    points routes each channel's gradient to ONE point, and a near-tie resolved differently by two fp32 implementations
+    moves whole rows of gradient — torch's own fp32 result is 7e-2 away from its fp64 result for seed 64, ours is 1e-5.)"""
+    import copy
+    import torch.nn.functional as F
+    from lpdnet_b200 import train
+    from lpdnet_b200.util.lpdnet_model import TranformNet
+    torch.manual_seed(k)
+    ops.set_precision("fp32")
+    B, N = 6, 200
+    net = TranformNet(k).cuda().train()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.2)
+    rows = torch.randn(B * N, k, device="cuda")
+    Wt = torch.randn(B, k, k, device="cuda")
+    n64 = copy.deepcopy(net).double()
+    h = rows.double().view(B, N, k).transpose(1, 2)
+    for conv, bn in ((n64.conv1, n64.bn1), (n64.conv2, n64.bn2), (n64.conv3, n64.bn3)):
+        h = F.relu(F.batch_norm(F.conv1d(h, conv.weight, conv.bias), None, None, bn.weight, bn.bias, True))
+    gl = h.max(2)[0]
+    for fc, bn in ((n64.fc1, n64.bn4), (n64.fc2, n64.bn5)):
+        gl = F.relu(F.batch_norm(F.linear(gl, fc.weight, fc.bias), None, None, bn.weight, bn.bias, True))
+    T = (F.linear(gl, n64.fc3.weight, n64.fc3.bias) + torch.eye(k, device="cuda", dtype=torch.double).view(1, -1)).view(B, k, k)
+    (T * Wt.double()).sum().backward()
+    ref = {n: p.grad.clone() for n, p in n64.named_parameters()}
+    tn, grads = train.TNetTrain(net), train._Grads()
+    with torch.no_grad():
+        Tm = tn.fwd(rows, k, B, N)
+        tn.bwd(Wt.clone(), grads, need_drows=(k == 64))
+    assert (Tm.double() - T.detach()).abs().max().item() <= 2e-4
+    gmax = max(float(r.abs().max()) for r in ref.values())
+    for n, p in net.named_parameters():
+        r, gm = ref[n], grads.by_param[p].double()
+        assert (gm - r).abs().max().item() <= 1e-4 * max(float(r.abs().max()), 1e-2 * gmax), n
