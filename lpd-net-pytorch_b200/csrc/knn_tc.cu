@@ -35,7 +35,7 @@ constexpr int KT_C = 64;           // candidates per stage (TMEM columns)
 constexpr int KT_SCAN_WARPS = 8;   // warps 0-7 scan/select (warp w: TMEM quadrant w % 4, column half w / 4)
 constexpr int KT_THREADS = 320;    // + warp 8 TMA, warp 9 MMA
 constexpr int KT_STRIDE = 257;     // list / queue words between slots: 256 (row, half) owners + 1 pad
-constexpr int KT_BSTAGES = 2;      // shared-memory candidate stages
+constexpr int KT_BSTAGES = 3;      // shared-memory candidate stages (the TMA round trip is ~3 MMA stage times)
 constexpr int KT_TSTAGES = 4;      // TMEM accumulator stages
 constexpr int KT_XSLOTS = 8;       // candidate-norm slots (>= BSTAGES + TSTAGES)
 

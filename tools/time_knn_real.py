@@ -25,7 +25,7 @@ x = synth.clouds(B, N).cuda()
 emb = model.emb_nn
 p = emb._prep.get(emb, emb._build)
 with torch.no_grad():
-    h, xyz, _, _ = emb._front(x, p, "LPDNet")
+    h, xyz, _, _ = emb._front(x, p, "LPDNet", True)
 feat = h.view(B, N, 64)
 print("feature norms: mean %.3f max %.3f" % (feat.norm(dim=2).mean().item(), feat.norm(dim=2).max().item()))
 lib = _lib.load()
