@@ -32,6 +32,8 @@ SIGNATURES = {
     "lpd_knn": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "lpd_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "lpd_knn_tc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "lpd_knn_tc_variant": (_i, [_i]),
+    "lpd_knn_tc_flags_offset": (_sz, [_i, _i, _i, _i]),
     "lpd_knn_xyz_workspace_bytes": (_sz, [_i, _i]),
     "lpd_knn_xyz": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "lpd_cell_order": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -419,9 +419,31 @@ struct KnnWs {
 }  // namespace tc
 }  // namespace lpd
 
+namespace lpd { namespace tc {
+size_t knn2_workspace_bytes(int B, int N, int k);
+size_t knn2_flags_offset(int B, int N, int k);
+int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes, int mt,
+             cudaStream_t st);
+// 0 = single-pass 3xTF32 replace-worst filter (this file); 1 / 2 = two-pass fp16 threshold filter (knn_tc2.cu) with
+// 128 / 256 query rows per work item.  Every variant returns the same (canonical) indices.
+static int g_knn_variant = 2;
+}}
+
+extern "C" int lpd_knn_tc_variant(int v) {
+    const int prev = lpd::tc::g_knn_variant;
+    if (v >= 0 && v <= 2) lpd::tc::g_knn_variant = v;
+    return prev;
+}
+
 extern "C" size_t lpd_knn_workspace_bytes(int B, int N, int C, int k) {
     if (B < 1 || N < 1 || C != 64 || k < 1 || k > 32) return 0;
-    return lpd::tc::KnnWs(B, N, k).total;
+    const size_t a = lpd::tc::KnnWs(B, N, k).total, b = lpd::tc::knn2_workspace_bytes(B, N, k);
+    return a > b ? a : b;
+}
+
+extern "C" size_t lpd_knn_tc_flags_offset(int B, int N, int C, int k) {
+    if (B < 1 || N < 1 || C != 64 || k < 1 || k > 32) return 0;
+    return lpd::tc::g_knn_variant == 0 ? lpd::tc::KnnWs(B, N, k).off_flags : lpd::tc::knn2_flags_offset(B, N, k);
 }
 
 extern "C" int lpd_knn_tc(const float* x, int B, int N, int C, int k, void* idx, int idx_i64,
@@ -432,12 +454,13 @@ extern "C" int lpd_knn_tc(const float* x, int B, int N, int C, int k, void* idx,
     LPD_REQUIRE((long long)B * N < (1ll << 31) / 128);
     LPD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 255) == 0);
     const tc::KnnWs W(B, N, k);
-    if (workspace_bytes < W.total) return LPD_EWORKSPACE;
+    if (workspace_bytes < lpd_knn_workspace_bytes(B, N, C, k)) return LPD_EWORKSPACE;
     int dev = 0, major = 0;
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return LPD_EUNSUPPORTED;
     cudaStream_t st = as_stream(stream);
+    if (tc::g_knn_variant != 0) return tc::knn2_run(x, B, N, k, idx, idx_i64, workspace, workspace_bytes, tc::g_knn_variant, st);
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     float* xxpad = reinterpret_cast<float*>(ws + W.off_xx);
     float* r2 = reinterpret_cast<float*>(ws + W.off_r2);

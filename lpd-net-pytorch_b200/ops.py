@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import (ACT_ADD, ACT_GATE, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, A_KM, A_MK, B_KN, B_NK)
 
-__all__ = ["bn_fold", "transpose", "knn", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
+__all__ = ["bn_fold", "transpose", "knn", "knn_tc_variant", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
            "gemm_tf32", "linear", "set_precision", "get_precision", "netvlad_assign", "softmax64", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
            "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ACT_SIGMOID", "ACT_GATE", "A_MK", "A_KM", "B_NK", "B_KN"]
 
@@ -87,16 +87,24 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-# C == 64: exact filter-and-refine kNN with the gram tiles on tcgen05 (lpd_knn_tc, 3xTF32 + canonical re-score).
-# Bit-identical to the CUDA-core kernel; rows whose candidate list cannot be proven complete are recomputed by it.
+# C == 64: exact filter-and-refine kNN with the gram tiles on tcgen05 (lpd_knn_tc: fp16 two-pass threshold filter, or the
+# 3xTF32 single-pass filter, + canonical fp32 re-score).  Bit-identical to the CUDA-core kernel; rows whose candidate list
+# cannot be proven complete are recomputed by it.
 KNN_TENSOR_CORES = True
 # C == 3: exact grid-accelerated kNN (lpd_knn_xyz); bit-identical to the brute-force scan of lpd_knn.
 KNN_GRID = True
 
 
-def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
+def knn_tc_variant(v: int = -1) -> int:
+    """Select the filter formulation of the tensor-core kNN (see lpd_knn_tc_variant in include/lpd_b200.h); returns the
+    previous one.  v = -1 only queries."""
+    return int(_lib.load().lpd_knn_tc_variant(int(v)))
+
+
+def knn(x_pm: torch.Tensor, k: int, int64: bool = False, diag: dict | None = None) -> torch.Tensor:
     """x_pm [B, N, C] point-major -> idx [B, N, k] (int32, or int64 for the public API), canonical order.
-    The result is bit-identical whichever kernel computes it."""
+    The result is bit-identical whichever kernel computes it.  `diag` (tests / tools): receives "flagged_tiles", the number
+    of 64-row tiles the tensor-core filter handed to the exact CUDA-core kernel (synchronises)."""
     lib = _lib.load()
     x_pm = _f32(x_pm, "x").contiguous()
     B, N, Cc = x_pm.shape
@@ -104,8 +112,12 @@ def knn(x_pm: torch.Tensor, k: int, int64: bool = False) -> torch.Tensor:
     if KNN_TENSOR_CORES and Cc == 64 and N >= 128 and x_pm.data_ptr() % 16 == 0:
         nbytes = lib.lpd_knn_workspace_bytes(B, N, Cc, k)
         ws = torch.empty((nbytes + 3) // 4, device=x_pm.device, dtype=torch.float32)
-        _call(f"lpd_knn_tc[C={Cc},k={k}]", 4, lib.lpd_knn_tc, x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64),
+        _call(f"lpd_knn_tc[C={Cc},k={k}]", 5, lib.lpd_knn_tc, x_pm.data_ptr(), B, N, Cc, k, idx.data_ptr(), int(int64),
               ws.data_ptr(), ws.numel() * 4, _stream())
+        if diag is not None:
+            off = lib.lpd_knn_tc_flags_offset(B, N, Cc, k) // 4
+            diag["flagged_tiles"] = int((ws.view(torch.int32)[off: off + B * ((N + 63) // 64)] != 0).sum().item())
+            diag["tiles"] = B * ((N + 63) // 64)
     elif KNN_GRID and Cc == 3 and N >= 64:
         nbytes = lib.lpd_knn_xyz_workspace_bytes(B, N)
         ws = torch.empty((nbytes + 3) // 4, device=x_pm.device, dtype=torch.float32)

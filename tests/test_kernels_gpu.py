@@ -329,14 +329,19 @@ def test_edgeconv_dg_tensor_core_path(cuda, B, N, k, C):
 
 
 # ------------------------------------------------------------------------------------------------ tensor-core kNN (exact)
+@pytest.mark.parametrize("variant", [2, 1, 0])
 @pytest.mark.parametrize("B,N,k,kind", [
     (2, 512, 20, "relu"), (3, 130, 20, "relu"), (1, 2048, 32, "relu"), (2, 1000, 24, "relu"), (2, 1000, 25, "relu"),
     (1, 4096, 20, "relu"), (1, 300, 20, "dups"), (1, 256, 20, "same"), (1, 640, 20, "big"), (1, 128, 1, "relu"),
-    (2, 700, 20, "clusters"),
+    (2, 700, 20, "clusters"), (2, 900, 20, "offset"), (1, 500, 20, "tiny"), (1, 500, 20, "huge"), (2, 1100, 32, "lattice"),
+    (3, 257, 20, "relu"), (1, 129, 32, "relu"),
 ])
-def test_knn_tensor_core_filter_refine_is_bit_exact(cuda, B, N, k, kind):
-    """lpd_knn_tc must return exactly the canonical neighbour lists, including on inputs built to defeat the TF32 filter
-    (duplicates, all-identical points, huge norms, tight clusters) where rows fall back to the exact kernel."""
+def test_knn_tensor_core_filter_refine_is_bit_exact(cuda, B, N, k, kind, variant):
+    """lpd_knn_tc must return exactly the canonical neighbour lists for every filter formulation, including on inputs
+    built to defeat the low-precision filter (duplicates, all-identical points, huge norms / offsets, tight clusters,
+    lattices with masses of exact ties, extreme scales) where rows fall back to the exact kernel.  On well-behaved inputs
+    the two-pass filter must resolve every tile itself (a filter that silently hands everything to the fallback would
+    still be exact, but is not the kernel under test)."""
     r = rng(N + k)
     x = np.maximum(r.standard_normal((B, N, 64)), 0.01 * r.standard_normal((B, N, 64))).astype(np.float32)
     if kind == "dups":
@@ -348,17 +353,60 @@ def test_knn_tensor_core_filter_refine_is_bit_exact(cuda, B, N, k, kind):
     elif kind == "clusters":
         centres = r.standard_normal((B, 7, 64)).astype(np.float32) * 3
         x = (centres[:, r.integers(0, 7, N)] + 1e-3 * r.standard_normal((B, N, 64))).astype(np.float32)
+    elif kind == "offset":
+        x = (x + 40.0).astype(np.float32)
+    elif kind == "tiny":
+        x = (x * 1e-12).astype(np.float32)
+    elif kind == "huge":
+        x = (x * 1e14).astype(np.float32)
+    elif kind == "lattice":
+        x = r.integers(0, 3, (B, N, 64)).astype(np.float32)
+        x[:, :, 8:] = 0
     want = knn_canonical(x, k)
     prev = ops.KNN_TENSOR_CORES
+    prev_variant = ops.knn_tc_variant(variant)
+    diag = {}
     try:
         ops.KNN_TENSOR_CORES = True
         ops.profile(True)
-        got = ops.knn(dev(x), k).cpu().numpy()
+        got = ops.knn(dev(x), k, diag=diag).cpu().numpy()
         labels = [l for l, _, _ in ops.profile(False)]
         ops.KNN_TENSOR_CORES = False
         got_simt = ops.knn(dev(x), k).cpu().numpy()                    # CUDA-core kernel, same bits
     finally:
         ops.KNN_TENSOR_CORES = prev
+        ops.knn_tc_variant(prev_variant)
     assert labels and labels[0].startswith("lpd_knn_tc")
-    assert np.array_equal(got, want)
     assert np.array_equal(got_simt, want)
+    assert np.array_equal(got, want), f"{int((got != want).any(axis=2).sum())} rows differ; diag {diag}"
+    if variant != 0 and kind in ("relu", "big", "offset", "tiny", "huge"):
+        assert diag["flagged_tiles"] == 0, diag
+
+
+def test_knn_tensor_core_variants_on_model_features(cuda):
+    """C2-like input (real conv2 features of a spatially ordered cloud, N=4096, k=20): all three formulations agree bit for
+    bit and the two-pass filter needs no fallback tile."""
+    from lpdnet_b200 import synth
+    from lpdnet_b200.util.PointNetVlad import PointNetVlad
+    B, N, k = 3, 4096, 20
+    model = PointNetVlad(num_points=N, featnet="lpdnet", emb_dims=1024)
+    model.load_state_dict(synth.synthetic_state_dict(model))
+    model = model.cuda().eval()
+    emb = model.emb_nn
+    p = emb._prep.get(emb, emb._build)
+    with torch.no_grad():
+        h, _, _, _ = emb._front(synth.clouds(B, N).cuda(), p, "LPDNet", True)
+    feat = h.view(B, N, 64).contiguous()
+    prev = ops.knn_tc_variant(-1)
+    out = {}
+    try:
+        for v in (0, 1, 2):
+            ops.knn_tc_variant(v)
+            diag = {}
+            out[v] = (ops.knn(feat, k, diag=diag).cpu().numpy(), diag)
+    finally:
+        ops.knn_tc_variant(prev)
+    want = knn_canonical(feat.cpu().numpy(), k)
+    for v in (0, 1, 2):
+        assert np.array_equal(out[v][0], want), f"variant {v}"
+    assert out[1][1]["flagged_tiles"] == 0 and out[2][1]["flagged_tiles"] == 0, (out[1][1], out[2][1])
