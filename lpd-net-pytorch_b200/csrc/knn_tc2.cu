@@ -52,6 +52,7 @@ constexpr int K2_XSLOTS = 16;    // candidate-norm slots (>= BSTAGES + TSTAGES)
 struct Knn2Params {
     const float* nrmpad;   // [B][Npad] centred squared norms, +inf padded   (storage order, like the operand rows)
     const float* snpad;    // [B][Npad] their square roots, 0 padded          (storage order)
+    const uint4* ext;      // [B][Npad/64][128] K-extension rows of the candidate tiles (2 KB per tile, core-matrix layout)
     const float* xxpad;    // [B][Npad] canonical squared norms               (point order)
     const float* r2;       // [B] max canonical squared norm
     const float* r2c;      // [B] max centred squared norm
@@ -69,6 +70,49 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// Warp-convergent issue: the WHOLE warp executes these with identical operands; elect.sync inside the asm picks the lane
+// that issues.  The control flow stays uniform and ptxas emits ELECT + one predicated UTCHMMA / UTCBAR / UTMALDG instead
+// of the elect-and-loop sequence it needs inside a divergent `if (lane == 0)` region (9-10 instructions per MMA there:
+// the single issuing thread was the bottleneck of the whole kernel).  `leader` is unused (kept for call-site clarity).
+__device__ __forceinline__ void tc_mma_f16_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                             uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_p(uint64_t* bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_p(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_p(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint64_t* bar, uint32_t bytes, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
 }
 // kind::f16 with fp16 operands (format 0), fp32 accumulate, A and B K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
@@ -142,7 +186,7 @@ knn2_center_kernel(const float* __restrict__ x, int N, float* __restrict__ mu, f
         if (g > 0.f) {
             int e;
             frexpf(g, &e);             // g = f * 2^e, f in [0.5, 1)
-            const int se = 15 - e;     // g * 2^se in [2^14, 2^15)
+            const int se = 8 - e;      // g * 2^se in [2^7, 2^8): the gram entries and sigma^2 nrm / 2 stay below 2^22
             if (!(g <= 3.0e38f) || se > 60 || se < -60) {
                 sigma = 1.f; c2 = __int_as_float(0x7fc00000);   // NaN: nothing is collected, every tile falls back
             } else {
@@ -158,8 +202,8 @@ knn2_center_kernel(const float* __restrict__ x, int N, float* __restrict__ mu, f
 // 0b. per point: fp16 centred operand row, both norms, per-cloud maxima
 __global__ void __launch_bounds__(256)
 knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ sc, int N, int Npad,
-                 __half* __restrict__ xh, float* __restrict__ xxpad, float* __restrict__ nrmpad, float* __restrict__ snpad,
-                 float* __restrict__ r2, float* __restrict__ r2c) {
+                 __half* __restrict__ xh, uint4* __restrict__ ext, float* __restrict__ xxpad, float* __restrict__ nrmpad,
+                 float* __restrict__ snpad, float* __restrict__ r2, float* __restrict__ r2c) {
     __shared__ float4 mus[16];
     const int b = blockIdx.y;
     if (threadIdx.x < 16) mus[threadIdx.x] = reinterpret_cast<const float4*>(mu + (size_t)b * 64)[threadIdx.x];
@@ -201,6 +245,29 @@ knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mu, cons
         atomicMax(reinterpret_cast<int*>(r2 + b), __float_as_int(acc));     // >= 0 (or NaN bits, harmless): int order == float order
         atomicMax(reinterpret_cast<int*>(r2c + b), __float_as_int(accc));
     }
+    // K-extension row of the candidate operand: the tensor core itself subtracts V = sigma^2 nrm / 2 from the gram entry,
+    //   t_ij = sigma^2 x'_i.x'_j - V_j = (sigma^2 / 2) a_ij,   V = 2^6 B1 + 2^-5 B2 + 2^-14 B3  (three fp16 pieces, residual
+    //   < 2^-15), against the constant query-side row [2^6, 2^-5, 2^-14, 2^15, 0...]; slot 3 pushes padded candidates to -2e9.
+    {
+        const float sigma = __ldg(sc + 2 * b);
+        float b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = -60000.f;
+        if (n < N) {
+            const float V = 0.5f * (sigma * sigma) * vn;
+            b1 = __half2float(__float2half_rn(V * 0.015625f));
+            const float r1 = __fmaf_rn(-b1, 64.f, V);
+            b2 = __half2float(__float2half_rn(r1 * 32.f));
+            const float rr = __fmaf_rn(-b2, 0.03125f, r1);
+            b3 = __half2float(__float2half_rn(rr * 16384.f));
+            b4 = 0.f;
+        }
+        const __half2 h01 = __floats2half2_rn(-b1, -b2), h23 = __floats2half2_rn(-b3, b4);
+        // no-swizzle K-major core-matrix layout of one 64-candidate tile (2 KB): 8-row groups 256 B apart, the two 8-column
+        // core matrices of a group 128 B apart, 16 B per row inside a core matrix
+        const int r = np & 63;
+        uint4* e = ext + ((size_t)b * (Npad >> 6) + (np >> 6)) * 128 + (r >> 3) * 16 + (r & 7);
+        e[0] = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23), 0u, 0u);
+        e[8] = make_uint4(0u, 0u, 0u, 0u);
+    }
     xxpad[(size_t)b * Npad + n] = vxx;            // canonical norms stay in point order (refine kernel)
     nrmpad[(size_t)b * Npad + np] = vn;           // centred norms follow the operand rows
     snpad[(size_t)b * Npad + np] = n < N ? sqrtf(vn) : 0.f;
@@ -236,6 +303,22 @@ __device__ __forceinline__ void bitonic_sort32_desc(float (&v)[32]) {
     }
 }
 
+// K-major operand WITHOUT swizzle (the 16-column K-extension): core matrices of 8 rows x 16 B, the two core matrices of
+// a row group 128 B apart (leading byte offset), row groups 256 B apart (stride byte offset)
+__device__ __forceinline__ uint64_t make_smem_desc_ext(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;                                              // layout type 0 = no swizzle
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 template <int MT>
 struct K2Smem {
     static constexpr int SCAN_THREADS = 256 * MT;
@@ -243,9 +326,12 @@ struct K2Smem {
     static constexpr uint32_t A_TILE = 128 * 128;         // one 128-row query tile: 64 fp16 = 128 B per row
     static constexpr uint32_t A_BYTES = MT * A_TILE;
     static constexpr uint32_t B_BYTES = K2_C * 128;
+    static constexpr uint32_t BX_BYTES = K2_C * 32;       // K-extension of a candidate tile
     static constexpr size_t off_b = 2 * A_BYTES;          // two query buffers (next item prefetched)
-    static constexpr size_t off_xs = off_b + K2_BSTAGES * B_BYTES;
-    static constexpr size_t off_ex = off_xs + K2_XSLOTS * 2 * K2_C * 4;      // per slot: 64 norms | 64 root norms
+    static constexpr size_t off_bx = off_b + K2_BSTAGES * B_BYTES;
+    static constexpr size_t off_ax = off_bx + K2_BSTAGES * BX_BYTES;         // constant query-side extension, 128 rows
+    static constexpr size_t off_xs = off_ax + 128 * 32;
+    static constexpr size_t off_ex = off_xs + K2_XSLOTS * K2_C * 4;          // per slot: 64 root norms (TIGHT only)
     static constexpr size_t off_bar = (off_ex + (size_t)32 * EXS * 4 + 7) / 8 * 8;
     static constexpr size_t total = off_bar + (4 + 2 * K2_BSTAGES + 2 * K2_TSTAGES) * 8 + 16;
     static_assert(total <= 227 * 1024, "knn2 shared memory budget");
@@ -261,6 +347,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* a_s = smem;
     uint8_t* b_s = smem + S::off_b;
+    uint8_t* bx_s = smem + S::off_bx;
+    uint8_t* ax_s = smem + S::off_ax;
     float* xs = reinterpret_cast<float*>(smem + S::off_xs);
     float* ex = reinterpret_cast<float*>(smem + S::off_ex);
     uint64_t* afull = reinterpret_cast<uint64_t*>(smem + S::off_bar);   // [2]
@@ -276,6 +364,15 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int nstages = 2 * P.ctiles;                      // per item: the candidate tiles twice
     const int full_blocks = P.N >> 6;                      // blocks below this one are stored scrambled
 
+    if (threadIdx.x < 128) {
+        // constant query-side K-extension [2^6, 2^-5, 2^-14, 2^15, 0 ...] in the no-swizzle core-matrix layout
+        const int r = threadIdx.x;
+        const __half2 h01 = __floats2half2_rn(64.f, 0.03125f), h23 = __floats2half2_rn(6.103515625e-05f, 32768.f);
+        uint4* e = reinterpret_cast<uint4*>(ax_s) + (r >> 3) * 16 + (r & 7);
+        e[0] = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23), 0u, 0u);
+        e[8] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+    }
     if (warp == SCAN_WARPS + 1) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -295,66 +392,72 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == SCAN_WARPS) {
-        // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        // ------------------------------ TMA producer (whole warp, lane 0 issues) ------------------------------
+        {
+            const uint32_t leader = lane == 0;
             uint32_t tcount = 0, icount = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++icount) {
                 const int b = item / P.qtiles, q0 = (item % P.qtiles) * (128 * MT);
                 const uint32_t ab = icount & 1, aph = (icount >> 1) & 1;
                 mbar_wait_sleep(&aempty[ab], aph ^ 1);
-                mbar_expect_tx(&afull[ab], S::A_BYTES);
+                mbar_expect_tx_p(&afull[ab], S::A_BYTES, leader);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
-                    tma_load_2d(a_s + ab * S::A_BYTES + mt * S::A_TILE, &tmap_a, &afull[ab], 0, b * P.N + q0 + mt * 128);
+                    tma_load_2d_p(a_s + ab * S::A_BYTES + mt * S::A_TILE, &tmap_a, &afull[ab], 0, b * P.N + q0 + mt * 128, leader);
+                const uint4* extb = P.ext + (size_t)b * (P.Npad >> 6) * 128;
+                const float* snb = P.snpad + (size_t)b * P.Npad;
+                uint32_t s = tcount % K2_BSTAGES, ph = (tcount / K2_BSTAGES) & 1, xsl = tcount % K2_XSLOTS;
                 for (int cs = 0; cs < nstages; ++cs, ++tcount) {
                     const int ct = cs >= P.ctiles ? cs - P.ctiles : cs;
-                    const uint32_t s = tcount % K2_BSTAGES, ph = (tcount / K2_BSTAGES) & 1;
                     mbar_wait_sleep(&bempty[s], ph ^ 1);
-                    mbar_expect_tx(&bfull[s], S::B_BYTES + (TIGHT ? 2 : 1) * K2_C * 4);
-                    tma_load_2d(b_s + s * S::B_BYTES, &tmap_b, &bfull[s], 0, b * P.N + ct * K2_C);
-                    float* slot = xs + (tcount % K2_XSLOTS) * 2 * K2_C;
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(slot)), "l"(P.nrmpad + (size_t)b * P.Npad + ct * K2_C),
-                                   "r"(K2_C * 4), "r"(smem_u32(&bfull[s])) : "memory");
-                    if (TIGHT)
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(smem_u32(slot + K2_C)), "l"(P.snpad + (size_t)b * P.Npad + ct * K2_C),
-                                       "r"(K2_C * 4), "r"(smem_u32(&bfull[s])) : "memory");
+                    mbar_expect_tx_p(&bfull[s], S::B_BYTES + S::BX_BYTES + (TIGHT ? K2_C * 4 : 0), leader);
+                    tma_load_2d_p(b_s + s * S::B_BYTES, &tmap_b, &bfull[s], 0, b * P.N + ct * K2_C, leader);
+                    bulk_load_p(bx_s + s * S::BX_BYTES, extb + (size_t)ct * 128, S::BX_BYTES, &bfull[s], leader);
+                    if (TIGHT) bulk_load_p(xs + xsl * K2_C, snb + ct * K2_C, K2_C * 4, &bfull[s], leader);
+                    if (++s == K2_BSTAGES) { s = 0; ph ^= 1; }
+                    xsl = (xsl + 1) % K2_XSLOTS;
                 }
             }
         }
     } else if (warp == SCAN_WARPS + 1) {
-        // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
+        // ------------------------------ MMA issuer (whole warp, lane 0 issues) ------------------------------
+        {
             constexpr uint32_t idesc = make_idesc_f16(128, K2_C);
+            const uint32_t leader = lane == 0;
+            const uint64_t dax = make_smem_desc_ext(smem_u32(ax_s));
             uint32_t tcount = 0, icount = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++icount) {
                 const uint32_t ab = icount & 1, aph = (icount >> 1) & 1;
                 mbar_wait_sleep(&afull[ab], aph);
-                const uint32_t a_addr = smem_u32(a_s + ab * S::A_BYTES);
+                const uint64_t da0 = make_smem_desc(smem_u32(a_s + ab * S::A_BYTES));
+                uint32_t s = tcount % K2_BSTAGES, ph = (tcount / K2_BSTAGES) & 1;
+                uint32_t ts = tcount % K2_TSTAGES, tph = (tcount / K2_TSTAGES) & 1;
                 for (int cs = 0; cs < nstages; ++cs, ++tcount) {
-                    const uint32_t s = tcount % K2_BSTAGES, ph = (tcount / K2_BSTAGES) & 1;
-                    const uint32_t ts = tcount % K2_TSTAGES, tph = (tcount / K2_TSTAGES) & 1;
                     mbar_wait_sleep(&tempty[ts], tph ^ 1);
                     mbar_wait_sleep(&bfull[s], ph);
                     tc_fence_after();
                     const uint64_t db = make_smem_desc(smem_u32(b_s + s * S::B_BYTES));
+                    const uint64_t dbx = make_smem_desc_ext(smem_u32(bx_s + s * S::BX_BYTES));
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        const uint64_t da = make_smem_desc(a_addr + mt * S::A_TILE);
+                        const uint64_t da = da0 + (uint64_t)(mt * (S::A_TILE >> 4));
                         const uint32_t d = tmem_base + ts * TCOLS + mt * K2_C;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)      // K = 64 = 4 x 16, 32 bytes per step inside the 128-byte swizzle atom
-                            tc_mma_f16(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, ks ? 1u : 0u);
+                            tc_mma_f16_p(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, ks ? 1u : 0u, leader);
+                        tc_mma_f16_p(d, dax, dbx, idesc, 1u, leader);   // K-extension: subtracts sigma^2 nrm_j / 2 (and buries the padding)
                     }
-                    tc_commit(&bempty[s]);
-                    tc_commit(&tfull[ts]);
+                    tc_commit_p(&bempty[s], leader);
+                    tc_commit_p(&tfull[ts], leader);
+                    if (++s == K2_BSTAGES) { s = 0; ph ^= 1; }
+                    if (++ts == K2_TSTAGES) { ts = 0; tph ^= 1; }
                 }
-                tc_commit(&aempty[ab]);   // all MMAs that read this query buffer have completed when this arrives
+                tc_commit_p(&aempty[ab], leader);   // all MMAs that read this query buffer have completed when this arrives
             }
         }
     } else {
         // ------------------------------ scan: one (stored query row, column half) per thread ------------------------------
+        // all scores below are t = (sigma^2 / 2) a: the power-of-two factor commutes with every comparison
         const int quad = warp & 3, half = (warp >> 2) & 1, mt = warp >> 3;
         const int own = mt * 256 + half * 128 + quad * 32 + lane;
         const int partner = own ^ 128;
@@ -370,9 +473,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 row = (srow & ~63) | ((((srow & 63) - bb) * inv_mod64(a)) & 63);
             }
             const bool live = srow < P.N;                              // (srow < N  <=>  row < N)
-            const float cb = __ldg(P.sc + 2 * b + 1);
+            const float inv_cb = 1.f / __ldg(P.sc + 2 * b + 1);        // sigma^2 / 2, a power of two (NaN: unusable cloud)
             float ni = 0.f, cni = 0.f;
-            if (live) { ni = sqrtf(__ldg(P.nrmpad + (size_t)b * P.Npad + srow)); cni = 2.5e-3f * ni; }
+            if (live) { ni = sqrtf(__ldg(P.nrmpad + (size_t)b * P.Npad + srow)); cni = 2.5e-3f * ni * inv_cb; }
             // ---------------- pass 1: running maximum of every column position ----------------
             float m[32];
 #pragma unroll
@@ -381,23 +484,24 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const uint32_t ts = tcount % K2_TSTAGES, tph = (tcount / K2_TSTAGES) & 1;
                 mbar_wait(&tfull[ts], tph);
                 tc_fence_after();
-                const float* xsj = xs + (tcount % K2_XSLOTS) * 2 * K2_C + half * 32;
                 uint32_t r[32];
                 tc_ld32(tmem_base + tm_lane + ts * TCOLS, r);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[ts]);
+                if (TIGHT) {                                                       // certified lower bounds
+                    const float* xsj = xs + (tcount % K2_XSLOTS) * K2_C + half * 32;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 xx = *reinterpret_cast<const float4*>(xsj + j);   // warp broadcast
-                    float a0 = fmaf(cb, __uint_as_float(r[j + 0]), -xx.x), a1 = fmaf(cb, __uint_as_float(r[j + 1]), -xx.y);
-                    float a2 = fmaf(cb, __uint_as_float(r[j + 2]), -xx.z), a3 = fmaf(cb, __uint_as_float(r[j + 3]), -xx.w);
-                    if (TIGHT) {                                                   // certified lower bounds
-                        const float4 sn = *reinterpret_cast<const float4*>(xsj + K2_C + j);
-                        a0 = fmaf(-cni, sn.x, a0); a1 = fmaf(-cni, sn.y, a1); a2 = fmaf(-cni, sn.z, a2); a3 = fmaf(-cni, sn.w, a3);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 sn = *reinterpret_cast<const float4*>(xsj + j);   // warp broadcast
+                        m[j + 0] = fmaxf(m[j + 0], fmaf(-cni, sn.x, __uint_as_float(r[j + 0])));
+                        m[j + 1] = fmaxf(m[j + 1], fmaf(-cni, sn.y, __uint_as_float(r[j + 1])));
+                        m[j + 2] = fmaxf(m[j + 2], fmaf(-cni, sn.z, __uint_as_float(r[j + 2])));
+                        m[j + 3] = fmaxf(m[j + 3], fmaf(-cni, sn.w, __uint_as_float(r[j + 3])));
                     }
-                    m[j + 0] = fmaxf(m[j + 0], a0); m[j + 1] = fmaxf(m[j + 1], a1);
-                    m[j + 2] = fmaxf(m[j + 2], a2); m[j + 3] = fmaxf(m[j + 3], a3);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], __uint_as_float(r[j]));
                 }
             }
             // ---------------- k-th largest of the row's 64 group maxima ----------------
@@ -417,10 +521,10 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const float xxi = __ldg(P.xxpad + (size_t)b * P.Npad + row);
                 const float r2 = __ldg(P.r2 + b), r2c = __ldg(P.r2c + b), sigma = __ldg(P.sc + 2 * b);
                 const float rc = sqrtf(r2c);
-                float eps = (1.9e-6f / sigma) * (ni + rc) + 9.5367431640625e-7f * (xxi + r2 + r2c);
-                if (!TIGHT) eps += cni * rc;
-                thr = fmaxf(tau0 - 2.f * eps, -3.0e38f);
-                if (!(eps < INFINITY)) thr = __int_as_float(0x7fc00000);   // unusable bound: collect nothing, fall back
+                float eps = (1.9e-6f / sigma) * (ni + rc) + 9.5367431640625e-7f * (xxi + r2) + 3.814697265625e-6f * r2c;
+                if (!TIGHT) eps += 2.5e-3f * ni * rc;
+                thr = fmaxf(tau0 - 2.f * eps * inv_cb, -1.0e9f);             // padded candidates sit near -2e9
+                if (!(eps * inv_cb < INFINITY)) thr = __int_as_float(0x7fc00000);   // unusable bound: collect nothing, fall back
             }
             // ---------------- pass 2: collect everything at or above the threshold ----------------
             int cnt = 0;
@@ -429,28 +533,33 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const uint32_t ts = tcount % K2_TSTAGES, tph = (tcount / K2_TSTAGES) & 1;
                 mbar_wait(&tfull[ts], tph);
                 tc_fence_after();
-                const float* xsj = xs + (tcount % K2_XSLOTS) * 2 * K2_C + half * 32;
                 uint32_t r[32];
                 tc_ld32(tmem_base + tm_lane + ts * TCOLS, r);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[ts]);
-                uint32_t mask = 0;
+                float u[32];
+                if (TIGHT) {                                                       // upper bounds
+                    const float* xsj = xs + (tcount % K2_XSLOTS) * K2_C + half * 32;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 xx = *reinterpret_cast<const float4*>(xsj + j);
-                    float a0 = fmaf(cb, __uint_as_float(r[j + 0]), -xx.x), a1 = fmaf(cb, __uint_as_float(r[j + 1]), -xx.y);
-                    float a2 = fmaf(cb, __uint_as_float(r[j + 2]), -xx.z), a3 = fmaf(cb, __uint_as_float(r[j + 3]), -xx.w);
-                    if (TIGHT) {                                                   // upper bounds
-                        const float4 sn = *reinterpret_cast<const float4*>(xsj + K2_C + j);
-                        a0 = fmaf(cni, sn.x, a0); a1 = fmaf(cni, sn.y, a1); a2 = fmaf(cni, sn.z, a2); a3 = fmaf(cni, sn.w, a3);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 sn = *reinterpret_cast<const float4*>(xsj + j);
+                        u[j + 0] = fmaf(cni, sn.x, __uint_as_float(r[j + 0])); u[j + 1] = fmaf(cni, sn.y, __uint_as_float(r[j + 1]));
+                        u[j + 2] = fmaf(cni, sn.z, __uint_as_float(r[j + 2])); u[j + 3] = fmaf(cni, sn.w, __uint_as_float(r[j + 3]));
                     }
-                    mask |= (a0 >= thr) ? (1u << (j + 0)) : 0u;
-                    mask |= (a1 >= thr) ? (1u << (j + 1)) : 0u;
-                    mask |= (a2 >= thr) ? (1u << (j + 2)) : 0u;
-                    mask |= (a3 >= thr) ? (1u << (j + 3)) : 0u;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(r[j]);
                 }
-                if (__any_sync(kFull, mask != 0)) {
+                // cheap test first: most (warp, tile) pairs hold no candidate at all (the rows of a warp are neighbours in
+                // space and so are the candidates of a tile)
+                float mx = fmaxf(u[30], u[31]);
+#pragma unroll
+                for (int j = 0; j < 30; j += 2) mx = fmax3(mx, u[j], u[j + 1]);
+                if (__any_sync(kFull, mx >= thr)) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask |= (u[j] >= thr) ? (1u << j) : 0u;
                     int pa = 1, pb = 0;                                  // undo the block's scrambling: c = (pos - b) a^-1
                     if (cs < full_blocks) { block_perm(cs, pa, pb); pa = inv_mod64(pa); }
                     const int jbase = cs * K2_C;
@@ -564,7 +673,7 @@ static int make_tmap_f16(CUtensorMap* m, const __half* base, long long rows, int
 static inline size_t align_up2(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Knn2Ws {
-    size_t off_xx, off_nrm, off_sn, off_r2, off_r2c, off_mu, off_sc, off_flags, off_xh, off_cnt, off_cand, total;
+    size_t off_xx, off_nrm, off_sn, off_ext, off_r2, off_r2c, off_mu, off_sc, off_flags, off_xh, off_cnt, off_cand, total;
     int npad, cap;
     Knn2Ws(int B, int N, int k) {
         npad = (N + 255) / 256 * 256;
@@ -573,6 +682,7 @@ struct Knn2Ws {
         off_xx = o; o = align_up2(o + (size_t)B * npad * 4, 256);
         off_nrm = o; o = align_up2(o + (size_t)B * npad * 4, 256);
         off_sn = o; o = align_up2(o + (size_t)B * npad * 4, 256);
+        off_ext = o; o = align_up2(o + (size_t)B * npad * 32, 256);
         off_r2 = o; o += (size_t)B * 4;
         off_r2c = o; o = align_up2(o + (size_t)B * 4, 256);
         off_mu = o; o = align_up2(o + (size_t)B * 64 * 4, 256);
@@ -620,7 +730,7 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     LPD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)B * ftiles * sizeof(int), st));
     knn2_center_kernel<<<B, 1024, 0, st>>>(x, N, mu, sc);
     LPD_LAUNCH_CHECK();
-    knn2_prep_kernel<<<dim3(ceil_div(W.npad, 256), B), 256, 0, st>>>(x, mu, sc, N, W.npad, xh, xxpad, nrmpad, snpad, r2, r2c);
+    knn2_prep_kernel<<<dim3(ceil_div(W.npad, 256), B), 256, 0, st>>>(x, mu, sc, N, W.npad, xh, reinterpret_cast<uint4*>(ws + W.off_ext), xxpad, nrmpad, snpad, r2, r2c);
     LPD_LAUNCH_CHECK();
     CUtensorMap ta, tb;
     int rc = make_tmap_f16(&ta, xh, (long long)B * N, 128);
@@ -628,7 +738,7 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     rc = make_tmap_f16(&tb, xh, (long long)B * N, K2_C);
     if (rc != LPD_OK) return rc;
     Knn2Params P;
-    P.nrmpad = nrmpad; P.snpad = snpad; P.xxpad = xxpad; P.r2 = r2; P.r2c = r2c; P.sc = sc;
+    P.nrmpad = nrmpad; P.snpad = snpad; P.ext = reinterpret_cast<const uint4*>(ws + W.off_ext); P.xxpad = xxpad; P.r2 = r2; P.r2c = r2c; P.sc = sc;
     P.cnt = reinterpret_cast<int*>(ws + W.off_cnt);
     P.cand = reinterpret_cast<int*>(ws + W.off_cand);
     P.B = B; P.N = N; P.Npad = W.npad; P.k = k;
