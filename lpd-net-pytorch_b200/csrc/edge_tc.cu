@@ -171,26 +171,24 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&yfull[grp]);
-                if (issuer) {
-                    // all six producer warps of the group run in lockstep on equal work, so this wait is short
-                    if (!w_ready) { mbar_wait(wfull, 0); w_ready = true; }
-                    mbar_wait_sleep(&tempty[grp], ph ^ 1);
-                    mbar_wait_sleep(&yfull[grp], ph);
-                    tc_fence_after();
-                    const uint32_t y_addr = smem_u32(y_s + grp * OP_BYTES);
+            if (lane == 0) mbar_arrive(&yfull[grp]);
+            if (issuer) {   // warp-uniform: the whole warp runs the issue sequence, elect.sync picks the lane (see tc_common.cuh)
+                // all six producer warps of the group run in lockstep on equal work, so this wait is short
+                if (!w_ready) { mbar_wait(wfull, 0); w_ready = true; }
+                mbar_wait_sleep(&tempty[grp], ph ^ 1);
+                mbar_wait_sleep(&yfull[grp], ph);
+                tc_fence_after();
+                const uint32_t y_addr = smem_u32(y_s + grp * OP_BYTES);
 #pragma unroll
-                    for (int kb2 = 0; kb2 < KB; ++kb2) {
-                        const uint64_t da = make_smem_desc(w_addr + kb2 * KB_BYTES), db = make_smem_desc(y_addr + kb2 * KB_BYTES);
+                for (int kb2 = 0; kb2 < KB; ++kb2) {
+                    const uint64_t da = make_smem_desc(w_addr + kb2 * KB_BYTES), db = make_smem_desc(y_addr + kb2 * KB_BYTES);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            tc_mma_tf32(tmem_base + grp * DG_ACC_STRIDE, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc,
-                                        (kb2 | ks) != 0 ? 1u : 0u);
-                    }
-                    tc_commit(&yempty[grp]);
-                    tc_commit(&tfull[grp]);
+                    for (int ks = 0; ks < 4; ++ks)
+                        tc_mma_tf32_e(tmem_base + grp * DG_ACC_STRIDE, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc,
+                                      (kb2 | ks) != 0 ? 1u : 0u);
                 }
+                tc_commit_e(&yempty[grp]);
+                tc_commit_e(&tfull[grp]);
             }
             __syncwarp();
         }

@@ -75,31 +75,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp, elect.sync picks the issuing lane (see tc_common.cuh)
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const int z = t / tiles_mn, tt = t % tiles_mn;
                 const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    mbar_expect_tx_e(&full[stage], STAGE_BYTES);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     if (TN) {
                         const int k0 = z * p.K + kb * BK;
 #pragma unroll
-                        for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * 4096, &tmap_a, &full[stage], m0 + i * 32, k0);
+                        for (int i = 0; i < BM / 32; ++i) tma_load_2d_e(sa + i * 4096, &tmap_a, &full[stage], m0 + i * 32, k0);
 #pragma unroll
-                        for (int i = 0; i < BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * 4096, &tmap_b, &full[stage], n0 + i * 32, k0);
+                        for (int i = 0; i < BN / 32; ++i) tma_load_2d_e(sa + A_BYTES + i * 4096, &tmap_b, &full[stage], n0 + i * 32, k0);
                     } else {
-                        tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m0);
-                        tma_load_2d(sa + A_BYTES, &tmap_b, &full[stage], kb * BK, n0);
+                        tma_load_2d_e(sa, &tmap_a, &full[stage], kb * BK, m0);
+                        tma_load_2d_e(sa + A_BYTES, &tmap_b, &full[stage], kb * BK, n0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, elect.sync picks the issuing lane (see tc_common.cuh)
             constexpr uint32_t idesc = make_idesc(BM, BN) | (TN ? ((1u << 15) | (1u << 16)) : 0u);   // a_major / b_major = MN
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -115,19 +115,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const uint64_t da = make_smem_desc_mn(sa), db = make_smem_desc_mn(sa + A_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)      // 8 k-rows (1024 B) per K=8 step
-                            tc_mma_tf32(tmem_d, da + (uint64_t)(k * 1024 >> 4), db + (uint64_t)(k * 1024 >> 4), idesc,
+                            tc_mma_tf32_e(tmem_d, da + (uint64_t)(k * 1024 >> 4), db + (uint64_t)(k * 1024 >> 4), idesc,
                                         (kb | k) != 0 ? 1u : 0u);
                     } else {
                         const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)
-                            tc_mma_tf32(tmem_d, da + (uint64_t)(k * UMMA_K * 4 >> 4), db + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
+                            tc_mma_tf32_e(tmem_d, da + (uint64_t)(k * UMMA_K * 4 >> 4), db + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
                                         (kb | k) != 0 ? 1u : 0u);
                     }
-                    tc_commit(&empty[stage]);           // slot reusable once these MMAs have read it
+                    tc_commit_e(&empty[stage]);           // slot reusable once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull[acc]);                 // accumulator complete
+                tc_commit_e(&tfull[acc]);                 // accumulator complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -584,17 +584,36 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 2. one warp per query row: canonical re-score of the collected candidates, rank, write the first k
+// The candidate rows are fetched COOPERATIVELY (coalesced: a half-warp reads 128 contiguous bytes of one candidate) into a
+// padded shared-memory tile, half a row (32 channels) at a time, and each lane then continues the canonical fmaf chain of
+// its own candidate out of shared memory (row stride 36 floats: the quarter-warp phases of LDS.128 hit distinct banks).
+// A lane-per-candidate gather straight from global memory costs up to 32 L1 wavefronts per load instruction and ran at
+// 90 % of the L1 wavefront peak.
+constexpr int RF_STRIDE = 36;
+constexpr int RF_WARPS = 8;
 template <int CAP>
-__global__ void __launch_bounds__(256)
+struct RefineSmem {
+    static constexpr size_t rows = (size_t)RF_WARPS * 32 * RF_STRIDE * 4;
+    static constexpr size_t off_xi = rows;
+    static constexpr size_t off_pd = off_xi + (size_t)RF_WARPS * 64 * 4;
+    static constexpr size_t off_id = off_pd + (size_t)RF_WARPS * 2 * CAP * 4;
+    static constexpr size_t total = off_id + (size_t)RF_WARPS * 2 * CAP * 4;
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(RF_WARPS * 32)
 knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad, const int* __restrict__ cnt,
                    const int* __restrict__ cand, int B, int N, int Npad, int k, void* __restrict__ idx_out, int idx_i64,
                    int* __restrict__ flags) {
     constexpr int E = (2 * CAP + 31) / 32;
-    __shared__ float s_pd[8][2 * CAP];
-    __shared__ int s_id[8][2 * CAP];
-    __shared__ float4 s_xi[8][16];
+    using S = RefineSmem<CAP>;
+    extern __shared__ __align__(16) uint8_t rsm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long grow = (long long)blockIdx.x * 8 + w;
+    float* s_rows = reinterpret_cast<float*>(rsm) + (size_t)w * 32 * RF_STRIDE;
+    float* s_xi = reinterpret_cast<float*>(rsm + S::off_xi) + w * 64;
+    float* s_pd = reinterpret_cast<float*>(rsm + S::off_pd) + w * 2 * CAP;
+    int* s_id = reinterpret_cast<int*>(rsm + S::off_id) + w * 2 * CAP;
+    const long long grow = (long long)blockIdx.x * RF_WARPS + w;
     if (grow >= (long long)B * N) return;
     const int b = (int)(grow / N), qi = (int)(grow % N);
     const int c0 = __ldg(cnt + grow * 2), c1 = __ldg(cnt + grow * 2 + 1);
@@ -603,7 +622,8 @@ knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad,
         if (lane == 0) flags[(size_t)b * ((N + 63) / 64) + qi / 64] = 1;
         return;
     }
-    if (lane < 16) s_xi[w][lane] = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * N + qi) * 64) + lane);
+    const float* xb = x + (size_t)b * N * 64;
+    reinterpret_cast<float2*>(s_xi)[lane] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)qi * 64) + lane);
     const float xxi = __ldg(xxpad + (size_t)b * Npad + qi);
     int id[E];
 #pragma unroll
@@ -612,27 +632,43 @@ knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad,
         id[e] = INT_MAX;
         if (s < total) id[e] = s < c0 ? __ldg(cand + (size_t)grow * 2 * CAP + s) : __ldg(cand + ((size_t)grow * 2 + 1) * CAP + (s - c0));
     }
-    __syncwarp();
+    const int hw = lane >> 4, hl = lane & 15;     // half-warp, lane inside it: a half-warp moves 32 channels of one candidate
     float pd[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        const int s = e * 32 + lane;
         pd[e] = -INFINITY;
-        if (s < total) {
-            const int j = id[e];
-            const float4* xj = reinterpret_cast<const float4*>(x + ((size_t)b * N + j) * 64);
+        if (e * 32 < total) {                     // warp-uniform
+            const int nc = min(32, total - e * 32);
             float dot = 0.f;
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
-                const float4 u = s_xi[w][g], v = __ldg(xj + g);
-                dot = __fmaf_rn(u.x, v.x, dot); dot = __fmaf_rn(u.y, v.y, dot);
-                dot = __fmaf_rn(u.z, v.z, dot); dot = __fmaf_rn(u.w, v.w, dot);
+            for (int ph = 0; ph < 2; ++ph) {
+                __syncwarp();                     // the previous tile has been consumed
+#pragma unroll 4
+                for (int c = 0; c < nc; c += 2) {
+                    const int j = __shfl_sync(kFull, id[e], min(c + hw, 31));
+                    if (c + hw < nc) {
+                        const float2 v = __ldg(reinterpret_cast<const float2*>(xb + (size_t)j * 64 + ph * 32) + hl);
+                        *reinterpret_cast<float2*>(s_rows + (c + hw) * RF_STRIDE + hl * 2) = v;
+                    }
+                }
+                __syncwarp();
+                if (lane < nc) {
+                    const float4* rj = reinterpret_cast<const float4*>(s_rows + lane * RF_STRIDE);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 u = reinterpret_cast<const float4*>(s_xi)[ph * 8 + g], v = rj[g];
+                        dot = __fmaf_rn(u.x, v.x, dot); dot = __fmaf_rn(u.y, v.y, dot);
+                        dot = __fmaf_rn(u.z, v.z, dot); dot = __fmaf_rn(u.w, v.w, dot);
+                    }
+                }
             }
-            const float xxj = __ldg(xxpad + (size_t)b * Npad + j);
-            const float t = -2.0f * dot;
-            pd[e] = __fsub_rn(__fsub_rn(-xxj, t), xxi);
-            s_pd[w][s] = pd[e];
-            s_id[w][s] = j;
+            if (lane < nc) {
+                const float xxj = __ldg(xxpad + (size_t)b * Npad + id[e]);
+                const float t = -2.0f * dot;
+                pd[e] = __fsub_rn(__fsub_rn(-xxj, t), xxi);
+                s_pd[e * 32 + lane] = pd[e];
+                s_id[e * 32 + lane] = id[e];
+            }
         }
     }
     __syncwarp();
@@ -643,8 +679,8 @@ knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad,
         if (e * 32 < total) {          // warp-uniform
             int rank = 0;
             for (int t = 0; t < total; ++t) {
-                const float pt = s_pd[w][t];
-                const int it = s_id[w][t];
+                const float pt = s_pd[t];
+                const int it = s_id[t];
                 rank += (pt > pd[e] || (pt == pd[e] && it < id[e])) ? 1 : 0;
             }
             if (s < total && rank < k) {
@@ -653,6 +689,17 @@ knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad,
             }
         }
     }
+}
+
+template <int CAP>
+static int knn2_refine_launch(const float* x, const float* xxpad, const int* cnt, const int* cand, int B, int N, int Npad, int k,
+                              void* idx, int idx_i64, int* flags, cudaStream_t st) {
+    const size_t smem = RefineSmem<CAP>::total;
+    LPD_CUDA_CHECK(allow_smem(knn2_refine_kernel<CAP>, smem));
+    const unsigned rblocks = (unsigned)(((long long)B * N + RF_WARPS - 1) / RF_WARPS);
+    knn2_refine_kernel<CAP><<<rblocks, RF_WARPS * 32, smem, st>>>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
 }
 
 // 2-D fp16 tensor [rows][64], box = [box_rows][64 cols = 128 B], 128B swizzle
@@ -747,10 +794,9 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     if (W.cap == 40) rc = (mt == 2) ? knn2_launch<2, 40, false>(ta, tb, P, st) : knn2_launch<1, 40, false>(ta, tb, P, st);
     else             rc = (mt == 2) ? knn2_launch<2, 64, true>(ta, tb, P, st) : knn2_launch<1, 64, true>(ta, tb, P, st);
     if (rc != LPD_OK) return rc;
-    const unsigned rblocks = (unsigned)(((long long)B * N + 7) / 8);
-    if (W.cap == 40) knn2_refine_kernel<40><<<rblocks, 256, 0, st>>>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags);
-    else             knn2_refine_kernel<64><<<rblocks, 256, 0, st>>>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags);
-    LPD_LAUNCH_CHECK();
+    rc = (W.cap == 40) ? knn2_refine_launch<40>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, st)
+                       : knn2_refine_launch<64>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, st);
+    if (rc != LPD_OK) return rc;
     return knn_simt64_flagged(x, B, N, k, idx, idx_i64, flags, st);   // exact recompute of flagged 64-row tiles only
 }
 
