@@ -33,6 +33,16 @@ UNIT = "submaps/s"
 BATCH, NPTS, KNN = 64, 4096, 20
 
 
+def ncu_traffic(label):
+    """DRAM bytes per launch of a kernel family from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by tools/ncu_traffic.py from dram__bytes_read.sum + dram__bytes_write.sum); None if not captured."""
+    try:
+        table = json.loads((Path(__file__).resolve().parent / "profiles" / "ncu_traffic.json").read_text())
+        return table.get(label, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -63,7 +73,42 @@ def kernel_work(label: str, B: int):
         return 0.0, 4.0 * B * N * (2 * C + C + k)
     if label == "lpd_netvlad_assign":
         return 2.0 * N * 1024 * 64 * B, 4.0 * B * N * (1024 + 64)
+    if label.startswith("lpd_knn_xyz"):
+        return 2.0 * N * N * 3 * B, 4.0 * B * N * (3 + k)
+    if label.startswith("lpd_edge_sel_stats") or label.startswith("lpd_edge_bwd_apply") or label.startswith("lpd_edge_bwd_reduce"):
+        # train-mode decomposed edge layer: per point the projected rows P, Q (C floats each) and k indices in, the selected
+        # row (C floats) + arg (C bytes) out / the gradient rows in and out; the N*k*C edge tensor counts zero
+        C = int(label.split("C=")[1].rstrip("]"))
+        return 0.0, B * N * (4.0 * (3 * C + k) + C)
+    if label.startswith("lpd_edge_materialize") or label.startswith("lpd_edge_sel_dense") or label.startswith("lpd_edge_dense_bwd_apply"):
+        C = int(label.split("C=")[1].rstrip("]"))
+        return 0.0, 4.0 * B * N * k * C       # the materialised [B*N*k][C] edge rows the DG2 backward needs, once
     return None
+
+
+def make_roofline(top, tot, cnt, step_ms, peaks, B):
+    """roofline object of the dominant kernel family: algorithmic FLOPs (or bytes) of ONE launch / its CUDA-event time.  The
+    bound is the tensor pipe when the algorithmic intensity is above the ridge of the measured peaks, HBM otherwise."""
+    work = kernel_work(top, B)
+    if work is None:
+        return {"kernel": top, "bound": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": ncu_traffic(top),
+                "share_of_step": tot[top] / step_ms, "ms_per_launch": tot[top] / cnt[top], "note": "no algorithmic work model for this kernel"}
+    flops, byts = work
+    per_launch_ms = tot[top] / cnt[top]
+    ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    if flops > 0 and flops / byts >= ridge:
+        tf = flops / (per_launch_ms * 1e-3) / 1e12
+        return {"kernel": top, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": tf / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(top),
+                "peak_source": peaks["source"] + ", bf16 sustained", "share_of_step": tot[top] / step_ms, "ms_per_launch": per_launch_ms,
+                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": byts,
+                "note": "algorithmic FLOPs per launch / CUDA-event time, graded against the dense bf16 tensor peak (an fp16/TF32 "
+                        "tensor-core kernel: its own peak is 1x / 0.5x of that; fp32 CUDA-core kernel: ~1/20)"}
+    gbs = byts / (per_launch_ms * 1e-3) / 1e9
+    return {"kernel": top, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "traffic": ncu_traffic(top), "peak_source": peaks["source"] + ", copy bandwidth", "share_of_step": tot[top] / step_ms,
+            "ms_per_launch": per_launch_ms, "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": byts,
+            "note": "algorithmic (compulsory) bytes per launch / CUDA-event time"}
 
 
 class ClockSampler:
@@ -267,16 +312,7 @@ def run_ours(args):
         breakdown = {k_: {"ms_per_step": round(v, 4), "share": round(v / step_ms, 4), "launches": cnt[k_]}
                      for k_, v in sorted(tot.items(), key=lambda kv: -kv[1])}
         top = max(tot, key=tot.get)
-        work = kernel_work(top, BATCH)
-        if work is not None:
-            flops, byts = work
-            per_launch_ms = tot[top] / cnt[top]
-            tf = flops / (per_launch_ms * 1e-3) / 1e12
-            roofline = {"kernel": top, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained",
-                        "share_of_step": tot[top] / step_ms, "ms_per_launch": per_launch_ms,
-                        "note": "algorithmic FLOPs per launch / CUDA-event time, graded against the dense bf16 tensor peak "
-                                "(TF32 tensor-core or fp32 CUDA-core kernel: its own peak is 1/2 resp. ~1/20 of that)"}
+        roofline = make_roofline(top, tot, cnt, step_ms, peaks, BATCH)
 
     if rank == 0:
         threads = os.cpu_count() or 1
@@ -453,14 +489,7 @@ def run_train(args):
         breakdown = {k_: {"ms_per_step": round(v, 4), "share": round(v / step_ms, 4), "launches": cnt[k_]}
                      for k_, v in sorted(tot.items(), key=lambda kv: -kv[1])[:24]}
         top = max(tot, key=tot.get)
-        work = kernel_work(top, TRAIN_CLOUDS)
-        if work is not None:
-            flops, byts = work
-            per_launch_ms = tot[top] / cnt[top]
-            tf = flops / (per_launch_ms * 1e-3) / 1e12
-            roofline = {"kernel": top, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained",
-                        "share_of_step": tot[top] / step_ms, "ms_per_launch": per_launch_ms}
+        roofline = make_roofline(top, tot, cnt, step_ms, peaks, TRAIN_CLOUDS)
         threads = os.cpu_count() or 1
         cpu_v, cpu_t = cpu_baseline_train(1, threads)
         nparams = sum(p.numel() for p in model.parameters())

@@ -90,16 +90,17 @@ int lpd_transpose(const float* in, float* out, int batch, int rows, int cols, vo
 int lpd_knn(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, void* stream);
 
 /* Same result as lpd_knn (bit-identical canonical order) for C == 64, with the distance GEMM on the tensor cores:
- * TF32 gram tiles (tcgen05) filter candidates, the survivors are re-scored in canonical fp32 arithmetic, and rows whose
- * candidate list cannot be proven complete fall back to the CUDA-core kernel.  `workspace`: device scratch of at least
+ * low-precision gram tiles (tcgen05) filter candidates, the survivors are re-scored in canonical fp32 arithmetic, and rows
+ * whose candidate list cannot be proven complete fall back to the CUDA-core kernel.  `workspace`: device scratch of at least
  * lpd_knn_workspace_bytes(B, N, C, k) bytes, 16-byte aligned.  Requires sm_100. */
 size_t lpd_knn_workspace_bytes(int B, int N, int C, int k);
 int lpd_knn_tc(const float* x, int B, int N, int C, int k, void* idx, int idx_i64,
                void* workspace, size_t workspace_bytes, void* stream);
 /* Filter formulation used by lpd_knn_tc (process-wide; returns the previous value, v outside 0..2 only queries):
  *   0  one pass, 3xTF32 gram, per-row replace-worst candidate lists (csrc/knn_tc.cu);
- *   1  two passes, fp16 gram of the centred features, strided group maxima -> provable threshold -> collect, 128 query
- *      rows per work item (csrc/knn_tc2.cu);   2  the same with 256 query rows per work item (default).
+ *   1  two passes, fp16 gram of the centred features with the norm folded into the MMA, strided group maxima -> provable
+ *      threshold -> collect, 128 query rows per work item (csrc/knn_tc2.cu; default);
+ *   2  the same with 256 query rows per work item.
  * The indices are bit-identical to lpd_knn for every variant. */
 int lpd_knn_tc_variant(int v);
 /* Diagnostics: byte offset, inside the workspace of the LAST lpd_knn_tc call with these sizes and the current variant, of

@@ -426,7 +426,7 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
              cudaStream_t st);
 // 0 = single-pass 3xTF32 replace-worst filter (this file); 1 / 2 = two-pass fp16 threshold filter (knn_tc2.cu) with
 // 128 / 256 query rows per work item.  Every variant returns the same (canonical) indices.
-static int g_knn_variant = 2;
+static int g_knn_variant = 1;
 }}
 
 extern "C" int lpd_knn_tc_variant(int v) {

@@ -6,34 +6,47 @@
 //
 //   0. knn2_center_kernel   per cloud: mean feature mu and a power-of-two scale sigma so that (x - mu) * sigma fits fp16.
 //      knn2_prep_kernel     per point: xh = fp16((x - mu) * sigma), centred norm nrm_j, canonical norm xx_j (fmaf chain of
-//                           lpd_knn), per-cloud maxima of both.  Distances are translation invariant, so the centring only
-//                           shrinks the operands (and with them the absolute rounding error of the fp16 gram).
-//   1. knn2_tc_kernel       per work item (one cloud, 128*MT query rows) the candidate tiles stream TWICE through
-//                           tcgen05.mma kind::f16 (fp32 accumulation in TMEM), score a_ij = 2 x'_i.x'_j - nrm_j:
-//        pass 1  every scan thread (one query row, one half of the 64 columns of a stage) keeps the running maximum of
-//                each of its 32 column positions: 64 "strided" groups per row (group = candidate index mod 64), no
-//                branches.  The k-th largest group maximum tau0 is a LOWER bound of the k-th best score of the row (k
-//                distinct candidates reach it).  It is found with an in-register bitonic sort of the 32 maxima, one
-//                exchange with the partner thread of the other column half, and a bitonic merge.
-//        pass 2  the same tiles again; every candidate with  a_ij >= tau0 - 2 eps_i  is appended to the row's list in
-//                global memory (index only).  With |a_ij - (canonical score + const_i)| <= eps_i this set provably holds
-//                the canonical top-k:  k candidates have canonical score >= tau0 - eps, so the canonical k-th score is
-//                >= tau0 - eps, and everything at or above it has a_ij >= tau0 - 2 eps.  The groups being strided, the
-//                spatially clustered neighbours fall in different groups and the set has ~1.4 k members.
+//                           lpd_knn), per-cloud maxima of both, and the 16-column "K-extension" of the candidate operand
+//                           (below).  Distances are translation invariant, so the centring only shrinks the operands (and
+//                           with them the absolute rounding error of the fp16 gram).
+//   1. knn2_tc_kernel       per work item (one cloud, 128*MT query rows) the candidates stream TWICE through tcgen05.mma
+//                           kind::f16 (fp32 accumulation in TMEM), 128 candidates (two 64-point blocks) per stage.  Each
+//                           stage is 4 MMAs over the 64 channels plus ONE MMA over the K-extension, whose operands
+//                           ([2^6, 2^-5, 2^-14, 2^15, 0..] on the query side, three fp16 pieces of -sigma^2 nrm_j / 2 and a
+//                           padding flag on the candidate side, no-swizzle core-matrix layout) make the tensor core itself
+//                           deliver the finished score  t_ij = (sigma^2 / 2) (2 x'_i.x'_j - nrm_j)  with padded candidates
+//                           at -2e9: the scan threads do no arithmetic on the scores, only comparisons.
+//        pass 1  every scan thread (one query row, 32 storage positions of both blocks of a stage) keeps the running
+//                maximum of each of its 32 positions: 64 "strided" groups per row (group = storage position inside the
+//                64-block), no branches.  The k-th largest group maximum tau0 is a LOWER bound of the k-th best score of
+//                the row (k distinct candidates reach it).  It is found with an in-register bitonic sort of the 32 maxima,
+//                one exchange with the partner thread of the other 32 positions, and a bitonic merge.  Pass 1 also records,
+//                per (warp, stage), D = min over the warp's 32 rows of (t_ii - best score of the row in the stage).
+//        pass 2  the same stages again; a warp whose table entry says no row can reach its threshold does not even read the
+//                accumulators (3 stages out of 4).  Otherwise every candidate with  t_ij >= tau0 - 2 eps_i  is appended to
+//                the row's list in global memory (index only).  With |t_ij - (canonical score + const_i)| <= eps_i this set
+//                provably holds the canonical top-k:  k candidates have canonical score >= tau0 - eps, so the canonical
+//                k-th score is >= tau0 - eps, and everything at or above it has t_ij >= tau0 - 2 eps.  The set has ~1.4 k
+//                members.
 //      Column scrambling: the host modules feed clouds in grid-cell order, where the neighbours of a point sit at index
 //      offsets that are near-multiples of the cell-row stride (64 points for N = 4096) and would pile up in the same
 //      groups.  knn2_prep_kernel therefore stores every full 64-point block under its own affine permutation of the 64
 //      positions (position = (a_t c + b_t) mod 64, a_t odd, hashed from the block number t); the scan maps hits back.
 //      TIGHT (k > 24): the error bound is applied per candidate, e_ij = 2.5e-3 |x'_i| |x'_j| instead of its maximum over j:
-//      pass 1 takes the maxima of the certified LOWER bounds a_ij - e_ij, pass 2 collects UPPER bounds a_ij + e_ij.
+//      pass 1 takes the maxima of the certified LOWER bounds t_ij - e_ij, pass 2 collects UPPER bounds t_ij + e_ij.
 //   2. knn2_refine_kernel   one warp per row: canonical fp32 re-score of the collected candidates (the arithmetic of
 //                           lpd_knn), rank by (pd descending, index ascending), first k written.
 //   3. rows whose list overflowed (masses of near-ties, e.g. duplicated points) or whose cloud could not be scaled flag
 //      their 64-row tile, which the exact CUDA-core kernel (knn.cu) recomputes.  Bit-identical to lpd_knn in every case.
 //
-// eps_i = 2.5e-3 |x'_i| R' + 1.9e-6 (|x'_i| + R') / sigma + 2^-20 (xx_i + max xx + R'^2):
+// eps_i (in units of a = 2 x'_i.x'_j - nrm_j) = 2.5e-3 |x'_i| R' + 1.9e-6 (|x'_i| + R') / sigma + 2^-20 (xx_i + max xx) + 2^-18 R'^2:
 //   fp16 rounding of both operands (2^-11 relative each, 2^-25 absolute for subnormals; factor 2 of the score; 28 % spare),
-//   the fp32 accumulation of the tensor core, and the rounding of the canonical chain itself (<= 19 ulp of the norms).
+//   the fp32 accumulation of the tensor core including the K-extension (<= 2^-21 of the largest term), and the rounding of
+//   the canonical chain itself (<= 19 ulp of the norms).
+//
+// What bounds it (ncu, B200, 64 clouds x 4096): the accumulators are read from TMEM at 64 B/clk/SM (4.3 GB in pass 1 alone
+// = 0.26 ms) and an SS-mode tcgen05.mma costs (128 + N)/4 clk of shared-memory operand reads on top of its N/2 clk of math,
+// which is why a stage is N = 128 wide; the single-thread roles issue through elect.sync (tc_common.cuh).
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -44,10 +57,12 @@ int knn_simt64_flagged(const float* x, int B, int N, int k, void* idx, int idx_i
 
 namespace tc {
 
-constexpr int K2_C = 64;         // candidates per stage (TMEM columns per 128-row query tile)
-constexpr int K2_BSTAGES = 6;    // shared-memory candidate stages (8 KB each)
-constexpr int K2_TSTAGES = 4;    // TMEM accumulator stages
-constexpr int K2_XSLOTS = 16;    // candidate-norm slots (>= BSTAGES + TSTAGES)
+constexpr int K2_C = 128;        // candidates per stage = two scrambled 64-blocks (TMEM columns per 128-row query tile);
+                                 // tcgen05.mma with N = 64 ran at a third of its rate (per-instruction overhead), N = 128 does not
+constexpr int K2_BSTAGES = 4;    // shared-memory candidate stages (16 + 4 KB each)
+constexpr int K2_TCOLS = 512;    // TMEM columns used: 512 / (128 * MT) accumulator stages
+constexpr int K2_XSLOTS = 12;    // candidate-norm slots (>= BSTAGES + TSTAGES + 3)
+constexpr int K2_TBL = 128;      // candidate stages per cloud the pass-2 skip table covers (N <= 16384; beyond: no skipping)
 
 struct Knn2Params {
     const float* nrmpad;   // [B][Npad] centred squared norms, +inf padded   (storage order, like the operand rows)
@@ -313,6 +328,28 @@ __device__ __forceinline__ uint64_t make_smem_desc_ext(uint32_t smem_addr) {
     d |= (uint64_t)1 << 46;
     return d;                                              // layout type 0 = no swizzle
 }
+// two 32-column TMEM loads (columns c .. c+31 and c+64 .. c+95) in flight, one wait
+__device__ __forceinline__ void tc_ld32x2(uint32_t taddr, uint32_t (&a)[32], uint32_t (&b)[32]) {
+#define LPD_LD32(R, ADDR)                                                                                               \
+    asm volatile(                                                                                                       \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                       \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                       \
+        : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]),              \
+          "=r"(R[8]), "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]),        \
+          "=r"(R[16]), "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]),      \
+          "=r"(R[24]), "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])       \
+        : "r"(ADDR))
+    LPD_LD32(a, taddr);
+    LPD_LD32(b, taddr + 64);
+#undef LPD_LD32
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// order-preserving float -> signed int key (for the integer warp reductions); NaN maps above +inf
+__device__ __forceinline__ int fkey(float v) {
+    const int b = __float_as_int(v);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -322,6 +359,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 template <int MT>
 struct K2Smem {
     static constexpr int SCAN_THREADS = 256 * MT;
+    static constexpr int TSTAGES = K2_TCOLS / (K2_C * MT);
     static constexpr int EXS = SCAN_THREADS + 1;          // exchange-buffer row stride (words)
     static constexpr uint32_t A_TILE = 128 * 128;         // one 128-row query tile: 64 fp16 = 128 B per row
     static constexpr uint32_t A_BYTES = MT * A_TILE;
@@ -332,8 +370,9 @@ struct K2Smem {
     static constexpr size_t off_ax = off_bx + K2_BSTAGES * BX_BYTES;         // constant query-side extension, 128 rows
     static constexpr size_t off_xs = off_ax + 128 * 32;
     static constexpr size_t off_ex = off_xs + K2_XSLOTS * K2_C * 4;          // per slot: 64 root norms (TIGHT only)
-    static constexpr size_t off_bar = (off_ex + (size_t)32 * EXS * 4 + 7) / 8 * 8;
-    static constexpr size_t total = off_bar + (4 + 2 * K2_BSTAGES + 2 * K2_TSTAGES) * 8 + 16;
+    static constexpr size_t off_tbl = off_ex + (size_t)32 * EXS * 4;        // [scan warp][K2_TBL] pass-1 tile margins
+    static constexpr size_t off_bar = (off_tbl + (size_t)8 * MT * K2_TBL * 4 + 7) / 8 * 8;
+    static constexpr size_t total = off_bar + (4 + 2 * K2_BSTAGES + 2 * TSTAGES) * 8 + 16;
     static_assert(total <= 227 * 1024, "knn2 shared memory budget");
 };
 
@@ -343,6 +382,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     using S = K2Smem<MT>;
     constexpr int SCAN_WARPS = 8 * MT;
     constexpr int TCOLS = K2_C * MT;                       // TMEM columns per accumulator stage
+    constexpr int K2_TSTAGES = S::TSTAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* a_s = smem;
@@ -351,6 +391,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* ax_s = smem + S::off_ax;
     float* xs = reinterpret_cast<float*>(smem + S::off_xs);
     float* ex = reinterpret_cast<float*>(smem + S::off_ex);
+    int* tbl = reinterpret_cast<int*>(smem + S::off_tbl);
     uint64_t* afull = reinterpret_cast<uint64_t*>(smem + S::off_bar);   // [2]
     uint64_t* aempty = afull + 2;                                       // [2]
     uint64_t* bfull = aempty + 2;
@@ -362,7 +403,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = P.B * P.qtiles;
     const int nstages = 2 * P.ctiles;                      // per item: the candidate tiles twice
-    const int full_blocks = P.N >> 6;                      // blocks below this one are stored scrambled
+    const int full_blocks = P.N >> 6;                      // 64-blocks below this one are stored scrambled
 
     if (threadIdx.x < 128) {
         // constant query-side K-extension [2^6, 2^-5, 2^-14, 2^15, 0 ...] in the no-swizzle core-matrix layout
@@ -412,7 +453,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     mbar_wait_sleep(&bempty[s], ph ^ 1);
                     mbar_expect_tx_p(&bfull[s], S::B_BYTES + S::BX_BYTES + (TIGHT ? K2_C * 4 : 0), leader);
                     tma_load_2d_p(b_s + s * S::B_BYTES, &tmap_b, &bfull[s], 0, b * P.N + ct * K2_C, leader);
-                    bulk_load_p(bx_s + s * S::BX_BYTES, extb + (size_t)ct * 128, S::BX_BYTES, &bfull[s], leader);
+                    bulk_load_p(bx_s + s * S::BX_BYTES, extb + (size_t)ct * 256, S::BX_BYTES, &bfull[s], leader);
                     if (TIGHT) bulk_load_p(xs + xsl * K2_C, snb + ct * K2_C, K2_C * 4, &bfull[s], leader);
                     if (++s == K2_BSTAGES) { s = 0; ph ^= 1; }
                     xsl = (xsl + 1) % K2_XSLOTS;
@@ -433,8 +474,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t s = tcount % K2_BSTAGES, ph = (tcount / K2_BSTAGES) & 1;
                 uint32_t ts = tcount % K2_TSTAGES, tph = (tcount / K2_TSTAGES) & 1;
                 for (int cs = 0; cs < nstages; ++cs, ++tcount) {
-                    mbar_wait_sleep(&tempty[ts], tph ^ 1);
-                    mbar_wait_sleep(&bfull[s], ph);
+                    mbar_wait(&tempty[ts], tph ^ 1);      // spin: __nanosleep wakes far too late for a 300-cycle stage
+                    mbar_wait(&bfull[s], ph);
                     tc_fence_after();
                     const uint64_t db = make_smem_desc(smem_u32(b_s + s * S::B_BYTES));
                     const uint64_t dbx = make_smem_desc_ext(smem_u32(bx_s + s * S::BX_BYTES));
@@ -461,6 +502,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int quad = warp & 3, half = (warp >> 2) & 1, mt = warp >> 3;
         const int own = mt * 256 + half * 128 + quad * 32 + lane;
         const int partner = own ^ 128;
+        // this thread's 64 columns: positions [32 half, 32 half + 32) of BOTH 64-blocks of a stage, so that group j of the thread
+        // is "storage position 32 half + j of every block" (64 distinct groups per row for the 64 points of any one block)
         const uint32_t tm_lane = ((uint32_t)(quad * 32) << 16) + mt * K2_C + half * 32;
         uint32_t tcount = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -474,9 +517,16 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             const bool live = srow < P.N;                              // (srow < N  <=>  row < N)
             const float inv_cb = 1.f / __ldg(P.sc + 2 * b + 1);        // sigma^2 / 2, a power of two (NaN: unusable cloud)
-            float ni = 0.f, cni = 0.f;
-            if (live) { ni = sqrtf(__ldg(P.nrmpad + (size_t)b * P.Npad + srow)); cni = 2.5e-3f * ni * inv_cb; }
-            // ---------------- pass 1: running maximum of every column position ----------------
+            float ni = 0.f, cni = 0.f, gself = 0.f;
+            if (live) {
+                const float ni2 = __ldg(P.nrmpad + (size_t)b * P.Npad + srow);
+                ni = sqrtf(ni2); cni = 2.5e-3f * ni * inv_cb;
+                gself = ni2 * inv_cb;                                  // ~ the row's own score t_ii: normalises the skip table
+            }
+            const bool use_tbl = P.ctiles <= K2_TBL;
+            int* wtbl = tbl + warp * K2_TBL;
+            const float ub_extra = TIGHT ? cni * sqrtf(__ldg(P.r2c + b)) : 0.f;   // TIGHT: upper bound of cni * sn_j
+            // ---------------- pass 1: running maximum of every column position (mod 32) ----------------
             float m[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) m[j] = -INFINITY;
@@ -484,24 +534,35 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const uint32_t ts = tcount % K2_TSTAGES, tph = (tcount / K2_TSTAGES) & 1;
                 mbar_wait(&tfull[ts], tph);
                 tc_fence_after();
-                uint32_t r[32];
-                tc_ld32(tmem_base + tm_lane + ts * TCOLS, r);
+                uint32_t r0[32], r1[32];
+                tc_ld32x2(tmem_base + tm_lane + ts * TCOLS, r0, r1);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[ts]);
-                if (TIGHT) {                                                       // certified lower bounds
+                float tm = -INFINITY;                                               // best raw score of the row in this block
+                if (TIGHT) {                                                        // certified lower bounds
                     const float* xsj = xs + (tcount % K2_XSLOTS) * K2_C + half * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 sn = *reinterpret_cast<const float4*>(xsj + j);   // warp broadcast
-                        m[j + 0] = fmaxf(m[j + 0], fmaf(-cni, sn.x, __uint_as_float(r[j + 0])));
-                        m[j + 1] = fmaxf(m[j + 1], fmaf(-cni, sn.y, __uint_as_float(r[j + 1])));
-                        m[j + 2] = fmaxf(m[j + 2], fmaf(-cni, sn.z, __uint_as_float(r[j + 2])));
-                        m[j + 3] = fmaxf(m[j + 3], fmaf(-cni, sn.w, __uint_as_float(r[j + 3])));
+                        const float4 s0 = *reinterpret_cast<const float4*>(xsj + j), s1 = *reinterpret_cast<const float4*>(xsj + 64 + j);
+                        m[j + 0] = fmax3(m[j + 0], fmaf(-cni, s0.x, __uint_as_float(r0[j + 0])), fmaf(-cni, s1.x, __uint_as_float(r1[j + 0])));
+                        m[j + 1] = fmax3(m[j + 1], fmaf(-cni, s0.y, __uint_as_float(r0[j + 1])), fmaf(-cni, s1.y, __uint_as_float(r1[j + 1])));
+                        m[j + 2] = fmax3(m[j + 2], fmaf(-cni, s0.z, __uint_as_float(r0[j + 2])), fmaf(-cni, s1.z, __uint_as_float(r1[j + 2])));
+                        m[j + 3] = fmax3(m[j + 3], fmaf(-cni, s0.w, __uint_as_float(r0[j + 3])), fmaf(-cni, s1.w, __uint_as_float(r1[j + 3])));
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) m[j] = fmax3(m[j], __uint_as_float(r0[j]), __uint_as_float(r1[j]));
+                }
+                if (use_tbl) {
+                    // skip table: D(warp, block) = min over the warp's rows of (t_ii - best score of the row in this block).  Pass 2
+                    // reads the block only if D <= max over the rows of (t_ii - threshold): any per-row constant keeps the
+                    // test exact-or-conservative, t_ii makes it tight (it removes the norm of the row from both sides).
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tm = fmax3(tm, __uint_as_float(r0[j]), __uint_as_float(r1[j]));
+                    const float D = live ? gself - (tm + ub_extra) : INFINITY;
+                    const int dk = __reduce_min_sync(kFull, fkey(D));
+                    if (lane == 0) wtbl[cs] = dk;
                 }
             }
             // ---------------- k-th largest of the row's 64 group maxima ----------------
@@ -527,46 +588,64 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (!(eps * inv_cb < INFINITY)) thr = __int_as_float(0x7fc00000);   // unusable bound: collect nothing, fall back
             }
             // ---------------- pass 2: collect everything at or above the threshold ----------------
+            const int dthr = __reduce_max_sync(kFull, fkey(live ? gself - thr : -INFINITY));
             int cnt = 0;
             int* mine = P.cand + (((size_t)b * P.N + (live ? row : 0)) * 2 + half) * CAP;
             for (int cs = 0; cs < P.ctiles; ++cs, ++tcount) {
                 const uint32_t ts = tcount % K2_TSTAGES, tph = (tcount / K2_TSTAGES) & 1;
                 mbar_wait(&tfull[ts], tph);
+                if (use_tbl && wtbl[cs] > dthr) {     // warp-uniform: no row of this warp has a candidate here
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[ts]);           // (after tfull: the arrival must land in this use's phase)
+                    continue;
+                }
                 tc_fence_after();
-                uint32_t r[32];
-                tc_ld32(tmem_base + tm_lane + ts * TCOLS, r);
+                uint32_t r0[32], r1[32];
+                tc_ld32x2(tmem_base + tm_lane + ts * TCOLS, r0, r1);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[ts]);
-                float u[32];
+                float u0[32], u1[32];
                 if (TIGHT) {                                                       // upper bounds
                     const float* xsj = xs + (tcount % K2_XSLOTS) * K2_C + half * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 sn = *reinterpret_cast<const float4*>(xsj + j);
-                        u[j + 0] = fmaf(cni, sn.x, __uint_as_float(r[j + 0])); u[j + 1] = fmaf(cni, sn.y, __uint_as_float(r[j + 1]));
-                        u[j + 2] = fmaf(cni, sn.z, __uint_as_float(r[j + 2])); u[j + 3] = fmaf(cni, sn.w, __uint_as_float(r[j + 3]));
+                        const float4 s0 = *reinterpret_cast<const float4*>(xsj + j), s1 = *reinterpret_cast<const float4*>(xsj + 64 + j);
+                        u0[j + 0] = fmaf(cni, s0.x, __uint_as_float(r0[j + 0])); u1[j + 0] = fmaf(cni, s1.x, __uint_as_float(r1[j + 0]));
+                        u0[j + 1] = fmaf(cni, s0.y, __uint_as_float(r0[j + 1])); u1[j + 1] = fmaf(cni, s1.y, __uint_as_float(r1[j + 1]));
+                        u0[j + 2] = fmaf(cni, s0.z, __uint_as_float(r0[j + 2])); u1[j + 2] = fmaf(cni, s1.z, __uint_as_float(r1[j + 2]));
+                        u0[j + 3] = fmaf(cni, s0.w, __uint_as_float(r0[j + 3])); u1[j + 3] = fmaf(cni, s1.w, __uint_as_float(r1[j + 3]));
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) { u0[j] = __uint_as_float(r0[j]); u1[j] = __uint_as_float(r1[j]); }
                 }
-                // cheap test first: most (warp, tile) pairs hold no candidate at all (the rows of a warp are neighbours in
-                // space and so are the candidates of a tile)
-                float mx = fmaxf(u[30], u[31]);
+                // cheap test first: even among the blocks the table lets through, most rows have no candidate
+                float mx = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 30; j += 2) mx = fmax3(mx, u[j], u[j + 1]);
+                for (int j = 0; j < 32; ++j) mx = fmax3(mx, u0[j], u1[j]);
                 if (__any_sync(kFull, mx >= thr)) {
-                    uint32_t mask = 0;
+                    uint32_t mask0 = 0, mask1 = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mask |= (u[j] >= thr) ? (1u << j) : 0u;
-                    int pa = 1, pb = 0;                                  // undo the block's scrambling: c = (pos - b) a^-1
-                    if (cs < full_blocks) { block_perm(cs, pa, pb); pa = inv_mod64(pa); }
-                    const int jbase = cs * K2_C;
-                    while (mask) {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        if (cnt < CAP) mine[cnt] = jbase + (((half * 32 + j - pb) * pa) & 63);
+                    for (int j = 0; j < 32; ++j) {
+                        mask0 |= (u0[j] >= thr) ? (1u << j) : 0u;
+                        mask1 |= (u1[j] >= thr) ? (1u << j) : 0u;
+                    }
+                    // undo the scrambling of the two blocks of the stage: c = (pos - b) a^-1
+                    int pa0 = 1, pb0 = 0, pa1 = 1, pb1 = 0;
+                    if (2 * cs < full_blocks) { block_perm(2 * cs, pa0, pb0); pa0 = inv_mod64(pa0); }
+                    if (2 * cs + 1 < full_blocks) { block_perm(2 * cs + 1, pa1, pb1); pa1 = inv_mod64(pa1); }
+                    const int jbase = cs * K2_C, pos0 = half * 32;
+                    while (mask0) {
+                        const int j = __ffs(mask0) - 1;
+                        mask0 &= mask0 - 1;
+                        if (cnt < CAP) mine[cnt] = jbase + (((pos0 + j - pb0) * pa0) & 63);
+                        ++cnt;
+                    }
+                    while (mask1) {
+                        const int j = __ffs(mask1) - 1;
+                        mask1 &= mask1 - 1;
+                        if (cnt < CAP) mine[cnt] = jbase + 64 + (((pos0 + j - pb1) * pa1) & 63);
                         ++cnt;
                     }
                 }
@@ -584,19 +663,21 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 2. one warp per query row: canonical re-score of the collected candidates, rank, write the first k
-// The candidate rows are fetched COOPERATIVELY (coalesced: a half-warp reads 128 contiguous bytes of one candidate) into a
-// padded shared-memory tile, half a row (32 channels) at a time, and each lane then continues the canonical fmaf chain of
-// its own candidate out of shared memory (row stride 36 floats: the quarter-warp phases of LDS.128 hit distinct banks).
-// A lane-per-candidate gather straight from global memory costs up to 32 L1 wavefronts per load instruction and ran at
-// 90 % of the L1 wavefront peak.
+// The candidate rows are fetched COOPERATIVELY (coalesced: a quarter-warp reads 128 contiguous bytes of one candidate with
+// LDG.128) into a padded shared-memory tile, half a row (32 channels) at a time, and each lane then continues the canonical
+// fmaf chain of its own candidate out of shared memory (row stride 36 floats: the quarter-warp phases of LDS.128 / STS.128
+// hit distinct banks).  A lane-per-candidate gather straight from global memory costs up to 32 L1 wavefronts per load
+// instruction and ran at 90 % of the L1 wavefront peak.  The final order is a rank count over 64-bit keys
+// (orderable(pd) << 32 | ~index: larger = better), two keys per LDS.128.
 constexpr int RF_STRIDE = 36;
 constexpr int RF_WARPS = 8;
 template <int CAP>
 struct RefineSmem {
+    static constexpr int KEYS = 2 * CAP + 2;      // + zero padding for the two-at-a-time rank loop
     static constexpr size_t rows = (size_t)RF_WARPS * 32 * RF_STRIDE * 4;
     static constexpr size_t off_xi = rows;
-    static constexpr size_t off_pd = off_xi + (size_t)RF_WARPS * 64 * 4;
-    static constexpr size_t off_id = off_pd + (size_t)RF_WARPS * 2 * CAP * 4;
+    static constexpr size_t off_key = off_xi + (size_t)RF_WARPS * 64 * 4;
+    static constexpr size_t off_id = off_key + (size_t)RF_WARPS * KEYS * 8;
     static constexpr size_t total = off_id + (size_t)RF_WARPS * 2 * CAP * 4;
 };
 
@@ -605,13 +686,12 @@ __global__ void __launch_bounds__(RF_WARPS * 32)
 knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad, const int* __restrict__ cnt,
                    const int* __restrict__ cand, int B, int N, int Npad, int k, void* __restrict__ idx_out, int idx_i64,
                    int* __restrict__ flags) {
-    constexpr int E = (2 * CAP + 31) / 32;
     using S = RefineSmem<CAP>;
     extern __shared__ __align__(16) uint8_t rsm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* s_rows = reinterpret_cast<float*>(rsm) + (size_t)w * 32 * RF_STRIDE;
     float* s_xi = reinterpret_cast<float*>(rsm + S::off_xi) + w * 64;
-    float* s_pd = reinterpret_cast<float*>(rsm + S::off_pd) + w * 2 * CAP;
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(rsm + S::off_key) + w * S::KEYS;
     int* s_id = reinterpret_cast<int*>(rsm + S::off_id) + w * 2 * CAP;
     const long long grow = (long long)blockIdx.x * RF_WARPS + w;
     if (grow >= (long long)B * N) return;
@@ -625,68 +705,60 @@ knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad,
     const float* xb = x + (size_t)b * N * 64;
     reinterpret_cast<float2*>(s_xi)[lane] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)qi * 64) + lane);
     const float xxi = __ldg(xxpad + (size_t)b * Npad + qi);
-    int id[E];
+    const int* l0 = cand + (size_t)grow * 2 * CAP;
+    for (int s = lane; s < total; s += 32) s_id[s] = s < c0 ? __ldg(l0 + s) : __ldg(l0 + CAP + (s - c0));
+    if (lane < 2) s_key[total + lane] = 0ull;     // padding keys: better than nothing
+    __syncwarp();
+    const int qw = lane >> 3, ql = lane & 7;      // quarter-warp and lane inside it: a quarter-warp moves 32 channels of one candidate
+    for (int base = 0; base < total; base += 32) {
+        const int nc = min(32, total - base);
+        const int myid = lane < nc ? s_id[base + lane] : 0;
+        float dot = 0.f;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int s = e * 32 + lane;
-        id[e] = INT_MAX;
-        if (s < total) id[e] = s < c0 ? __ldg(cand + (size_t)grow * 2 * CAP + s) : __ldg(cand + ((size_t)grow * 2 + 1) * CAP + (s - c0));
-    }
-    const int hw = lane >> 4, hl = lane & 15;     // half-warp, lane inside it: a half-warp moves 32 channels of one candidate
-    float pd[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        pd[e] = -INFINITY;
-        if (e * 32 < total) {                     // warp-uniform
-            const int nc = min(32, total - e * 32);
-            float dot = 0.f;
-#pragma unroll
-            for (int ph = 0; ph < 2; ++ph) {
-                __syncwarp();                     // the previous tile has been consumed
-#pragma unroll 4
-                for (int c = 0; c < nc; c += 2) {
-                    const int j = __shfl_sync(kFull, id[e], min(c + hw, 31));
-                    if (c + hw < nc) {
-                        const float2 v = __ldg(reinterpret_cast<const float2*>(xb + (size_t)j * 64 + ph * 32) + hl);
-                        *reinterpret_cast<float2*>(s_rows + (c + hw) * RF_STRIDE + hl * 2) = v;
-                    }
-                }
-                __syncwarp();
-                if (lane < nc) {
-                    const float4* rj = reinterpret_cast<const float4*>(s_rows + lane * RF_STRIDE);
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float4 u = reinterpret_cast<const float4*>(s_xi)[ph * 8 + g], v = rj[g];
-                        dot = __fmaf_rn(u.x, v.x, dot); dot = __fmaf_rn(u.y, v.y, dot);
-                        dot = __fmaf_rn(u.z, v.z, dot); dot = __fmaf_rn(u.w, v.w, dot);
-                    }
-                }
+        for (int ph = 0; ph < 2; ++ph) {
+            __syncwarp();                         // the previous tile has been consumed
+            for (int c = qw; c < nc; c += 4) {
+                const int j = s_id[base + c];
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * 64 + ph * 32) + ql);
+                *reinterpret_cast<float4*>(s_rows + c * RF_STRIDE + ql * 4) = v;
             }
+            __syncwarp();
             if (lane < nc) {
-                const float xxj = __ldg(xxpad + (size_t)b * Npad + id[e]);
-                const float t = -2.0f * dot;
-                pd[e] = __fsub_rn(__fsub_rn(-xxj, t), xxi);
-                s_pd[e * 32 + lane] = pd[e];
-                s_id[e * 32 + lane] = id[e];
+                const float4* rj = reinterpret_cast<const float4*>(s_rows + lane * RF_STRIDE);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float4 u = reinterpret_cast<const float4*>(s_xi)[ph * 8 + g], v = rj[g];
+                    dot = __fmaf_rn(u.x, v.x, dot); dot = __fmaf_rn(u.y, v.y, dot);
+                    dot = __fmaf_rn(u.z, v.z, dot); dot = __fmaf_rn(u.w, v.w, dot);
+                }
             }
+        }
+        if (lane < nc) {
+            const float xxj = __ldg(xxpad + (size_t)b * Npad + myid);
+            const float t = -2.0f * dot;
+            const float pd = __fadd_rn(__fsub_rn(__fsub_rn(-xxj, t), xxi), 0.0f);   // (+ 0: -0.0 and +0.0 must share one key)
+            uint32_t u = __float_as_uint(pd);
+            u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;                  // monotone float -> uint
+            s_key[base + lane] = ((unsigned long long)u << 32) | (uint32_t)(~myid);
         }
     }
     __syncwarp();
     const size_t o = (size_t)grow * k;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int s = e * 32 + lane;
-        if (e * 32 < total) {          // warp-uniform
-            int rank = 0;
-            for (int t = 0; t < total; ++t) {
-                const float pt = s_pd[t];
-                const int it = s_id[t];
-                rank += (pt > pd[e] || (pt == pd[e] && it < id[e])) ? 1 : 0;
-            }
-            if (s < total && rank < k) {
-                if (idx_i64) reinterpret_cast<long long*>(idx_out)[o + rank] = id[e];
-                else reinterpret_cast<int*>(idx_out)[o + rank] = id[e];
-            }
+    const int npairs = (total + 1) >> 1;
+    for (int base = 0; base < total; base += 32) {
+        const int s = base + lane;
+        const unsigned long long mine = s < total ? s_key[s] : ~0ull;
+        int rank = 0;
+        const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(s_key);
+#pragma unroll 4
+        for (int t = 0; t < npairs; ++t) {
+            const ulonglong2 kk = kp[t];                                 // warp broadcast
+            rank += (kk.x > mine) + (kk.y > mine);
+        }
+        if (s < total && rank < k) {
+            const int id = (int)~(uint32_t)mine;
+            if (idx_i64) reinterpret_cast<long long*>(idx_out)[o + rank] = id;
+            else reinterpret_cast<int*>(idx_out)[o + rank] = id;
         }
     }
 }
@@ -782,7 +854,7 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     CUtensorMap ta, tb;
     int rc = make_tmap_f16(&ta, xh, (long long)B * N, 128);
     if (rc != LPD_OK) return rc;
-    rc = make_tmap_f16(&tb, xh, (long long)B * N, K2_C);
+    rc = make_tmap_f16(&tb, xh, (long long)B * N, K2_C);      // 128 candidates per stage
     if (rc != LPD_OK) return rc;
     Knn2Params P;
     P.nrmpad = nrmpad; P.snpad = snpad; P.ext = reinterpret_cast<const uint4*>(ws + W.off_ext); P.xxpad = xxpad; P.r2 = r2; P.r2c = r2c; P.sc = sc;
