@@ -1,0 +1,69 @@
+"""SURVEY §8f "next" rows: submap file format, hard-negative mining, feature representation / update_vectors."""
+import numpy as np
+import pytest
+import torch
+
+from lpdnet_b200 import loading_pointclouds as lp
+
+
+def test_bin_loader_round_trip_and_wrong_size(tmp_path):
+    """reference loading_pointclouds.py:26-47: float64 raw file of 4096 x 3; other sizes are reported and skipped"""
+    r = np.random.default_rng(5)
+    good = r.uniform(-1, 1, (4096, 3))
+    bad = r.uniform(-1, 1, (1000, 3))
+    good.astype(np.float64).tofile(tmp_path / "a.bin")
+    bad.astype(np.float64).tofile(tmp_path / "b.bin")
+    (good * 2).astype(np.float64).tofile(tmp_path / "c.bin")
+    pc = lp.load_pc_file("a.bin", str(tmp_path))
+    assert pc.dtype == np.float64 and pc.shape == (4096, 3) and np.array_equal(pc, good)
+    assert lp.load_pc_file("b.bin", str(tmp_path)).shape == (0,)
+    pcs = lp.load_pc_files(["a.bin", "b.bin", "c.bin"], str(tmp_path))
+    assert pcs.shape == (2, 4096, 3) and np.array_equal(pcs[1], good * 2)
+    x = lp.to_model_input(pcs)
+    assert x.dtype == np.float32 and x.shape == (2, 1, 4096, 3) and x.flags["C_CONTIGUOUS"]
+    assert np.array_equal(x[0, 0], good.astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_hard_negative_mining_matches_kdtree(cuda):
+    """reference util/data.py:103-115: KDTree over the cached descriptors of the sampled negatives"""
+    from sklearn.neighbors import KDTree
+    from lpdnet_b200.util import data
+    r = np.random.default_rng(11)
+    table = r.standard_normal((5000, 256)).astype(np.float32)
+    table /= np.linalg.norm(table, axis=1, keepdims=True)
+    for trial in range(4):
+        negs = r.choice(5000, size=2000, replace=False).tolist()
+        q = table[r.integers(0, 5000)] + 0.05 * r.standard_normal(256).astype(np.float32)
+        want = np.squeeze(np.array(negs)[KDTree(table[negs]).query(np.array([q]), k=10)[1][0]]).tolist()
+        assert data.get_random_hard_negatives(q, negs, 10, latent_vectors=table) == want
+        data.TRAINING_LATENT_VECTORS = table          # the reference's global
+        assert data.get_random_hard_negatives(q, negs, 10) == want
+    qs = table[:3] + 0.05 * r.standard_normal((3, 256)).astype(np.float32)
+    lists = [r.choice(5000, size=500, replace=False).tolist() for _ in range(3)]
+    got = data.hard_negatives_batch(qs, torch.from_numpy(table), lists, 7)
+    for i in range(3):
+        want = np.array(lists[i])[KDTree(table[lists[i]]).query(qs[i:i + 1], k=7)[1][0]].tolist()
+        assert got[i] == want
+
+
+@pytest.mark.gpu
+def test_feature_representation_and_update_vectors(cuda):
+    """reference util/data.py:117-133, :277-354: single-submap and bulk embedding agree with the batched model call and
+    leave the model in train mode"""
+    from lpdnet_b200 import synth
+    from lpdnet_b200.util import data
+    from lpdnet_b200.util.PointNetVlad import PointNetVlad
+    model = PointNetVlad(num_points=1024, featnet="lpdnet", emb_dims=1024)
+    model.load_state_dict(synth.synthetic_state_dict(model))
+    model = model.cuda().eval()
+    clouds = synth.clouds(5, 1024)[:, 0].numpy()
+    with torch.no_grad():
+        want = model(torch.from_numpy(clouds).unsqueeze(1).cuda()).cpu().numpy()
+    one = data.get_feature_representation(clouds[2], model)
+    assert model.training and one.shape == (256,)
+    assert np.abs(one - want[2]).max() < 1e-5
+    model.eval()
+    vecs = data.update_vectors(model, clouds, batch_num=2)      # ragged tail batch
+    assert model.training and vecs.shape == (5, 256) and data.TRAINING_LATENT_VECTORS is vecs
+    assert np.abs(vecs - want).max() < 1e-5
