@@ -60,8 +60,10 @@ def kernel_work(label: str, B: int):
         M, Nn, K, batch = (int(v) for v in label[9:-1].split("x"))
         return 2.0 * M * Nn * K * batch, 4.0 * batch * (M * K + Nn * K + M * Nn)
     if label.startswith("lpd_gemm_tf32["):
-        M, Nn, K = (int(v) for v in label[14:-1].split("x"))
-        return 2.0 * M * Nn * K, 4.0 * (M * K + Nn * K + M * Nn)
+        dims = [int(v) for v in label[14:-1].split("x")]
+        M, Nn, K = dims[:3]
+        batch = dims[3] if len(dims) > 3 else 1
+        return 2.0 * M * Nn * K * batch, 4.0 * batch * (M * K + Nn * K + M * Nn)
     if label.startswith("lpd_knn[C=64") or label.startswith("lpd_knn_tc[C=64"):
         return 2.0 * N * N * 64 * B, 4.0 * B * N * (64 + k)
     if label.startswith("lpd_knn[C=3"):

@@ -151,6 +151,13 @@ int lpd_gemm(const float* A, int a_layout, int lda, long long strideA,
 int lpd_gemm_tf32(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                   int M, int N, int K, const float* scale, const float* shift, int act, float slope,
                   void* stream);
+/* The same kernel, batched and / or accumulating (training backward: the per-cloud NetVLAD products
+ * da[b] = F[b] dvraw[b], dF[b] += a[b] dvraw[b]^T of PointNetVlad.py:64-68's backward, and input gradients that add into an
+ * existing buffer):  C[z*M + m][n] (+)= act(scale[n] * sum_k A[z*M + m][k] * B[z*N + n][k] + shift[n]),  z < batch.
+ * A [batch*M][lda], B [batch*N][ldb], C [batch*M][ldc] are the per-slice matrices stacked on their row axis. */
+int lpd_gemm_tf32_ex(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                     int M, int N, int K, int batch, int accumulate, const float* scale, const float* shift, int act,
+                     float slope, void* stream);
 
 /* Tensor-core GEMM contracting over the ROWS of two point-major maps (both operands "MN-major" for the tensor core):
  *     C[z][m][n] = sum_{k < K} A[z*K + k][m] * B[z*K + k][n]        A [batch*K][lda], B [batch*K][ldb]

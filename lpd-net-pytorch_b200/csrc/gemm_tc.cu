@@ -30,7 +30,9 @@ struct Params {
     const float* scale; const float* shift;
     float neg_slope;   // act(v) = max(v, v * neg_slope): 1 -> identity, 0 -> ReLU, 0 < s < 1 -> LeakyReLU(s)
     int tiles_m, tiles_n;
-    int batch; long long strideC;   // TN only: slice z contracts rows [z*K, (z+1)*K) of both operands into C + z*strideC
+    int batch; long long strideC;   // TN: slice z contracts rows [z*K, (z+1)*K) of both operands into C + z*strideC
+    int bM, bN;                     // !TN, batch > 1: slice z multiplies rows [z*bM, ..) of A with rows [z*bN, ..) of B into C rows z*bM ..
+    int accumulate;                 // !TN: C += result (the epilogue reads C)
 };
 
 // TN == false:  C[m][n] = sum_k A[m][k] B[n][k]      (both operands K-contiguous: "K-major" UMMA tiles)
@@ -56,7 +58,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + BK - 1) / BK;
     const int tiles_mn = p.tiles_m * p.tiles_n;
-    const int num_tiles = tiles_mn * (TN ? p.batch : 1);
+    const int num_tiles = tiles_mn * p.batch;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -91,8 +93,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < BN / 32; ++i) tma_load_2d_e(sa + A_BYTES + i * 4096, &tmap_b, &full[stage], n0 + i * 32, k0);
                     } else {
-                        tma_load_2d_e(sa, &tmap_a, &full[stage], kb * BK, m0);
-                        tma_load_2d_e(sa + A_BYTES, &tmap_b, &full[stage], kb * BK, n0);
+                        tma_load_2d_e(sa, &tmap_a, &full[stage], kb * BK, z * p.bM + m0);
+                        tma_load_2d_e(sa + A_BYTES, &tmap_b, &full[stage], kb * BK, z * p.bN + n0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -163,7 +165,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
                     if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
                 }
-                float* gcol = p.C + (TN ? (size_t)z * p.strideC : (size_t)0) + (size_t)row0 * p.ldc + col;
+                float* gcol = p.C + (TN ? (size_t)z * p.strideC : (size_t)z * p.bM * p.ldc) + (size_t)row0 * p.ldc + col;
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int rr = it * 4 + rsub;
@@ -171,7 +173,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
                     v.x = fmaxf(v.x, v.x * p.neg_slope); v.y = fmaxf(v.y, v.y * p.neg_slope);
                     v.z = fmaxf(v.z, v.z * p.neg_slope); v.w = fmaxf(v.w, v.w * p.neg_slope);
-                    if (col_ok && row0 + rr < p.M) *reinterpret_cast<float4*>(gcol + (size_t)rr * p.ldc) = v;
+                    if (col_ok && row0 + rr < p.M) {
+                        float4* dstp = reinterpret_cast<float4*>(gcol + (size_t)rr * p.ldc);
+                        if (!TN && p.accumulate) { const float4 o = *dstp; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        *dstp = v;
+                    }
                 }
                 __syncwarp();                            // staging buffer is rewritten by the next chunk
             }
@@ -198,7 +204,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaSt
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     p.tiles_m = ceil_div(p.M, BM);
     p.tiles_n = ceil_div(p.N, BN);
-    const long long tiles = (long long)p.tiles_m * p.tiles_n * (TN ? p.batch : 1);
+    const long long tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
     const int grid = (int)(tiles < sms ? tiles : sms);
     gemm_tf32_kernel<BN, STAGES, TN><<<grid, THREADS, smem, st>>>(ta, tb, p);
     LPD_LAUNCH_CHECK();
@@ -208,34 +214,42 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaSt
 }  // namespace tc
 }  // namespace lpd
 
-extern "C" int lpd_gemm_tf32(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                             int M, int N, int K, const float* scale, const float* shift, int act, float slope,
-                             void* stream) {
+extern "C" int lpd_gemm_tf32_ex(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                                int M, int N, int K, int batch, int accumulate, const float* scale, const float* shift, int act,
+                                float slope, void* stream) {
     using namespace lpd;
-    LPD_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1);
+    LPD_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1 && batch >= 1);
     LPD_REQUIRE(lda >= K && ldb >= K && ldc >= N);
     LPD_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0);          // 16-byte global strides (TMA) / float4 stores
     LPD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0);
     LPD_REQUIRE((N % 4) == 0);
     LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || (act == LPD_ACT_LEAKY && slope >= 0.f && slope <= 1.f));
+    LPD_REQUIRE((long long)batch * M < (1ll << 31) && (long long)batch * N < (1ll << 31));
     int dev = 0, major = 0;
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return LPD_EUNSUPPORTED;
     const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     CUtensorMap ta, tb;
-    int rc = tc::make_tmap(&ta, A, M, K, lda, tc::BM);
+    int rc = tc::make_tmap(&ta, A, (long long)batch * M, K, lda, tc::BM);
     if (rc != LPD_OK) return rc;
-    rc = tc::make_tmap(&tb, B, N, K, ldb, BN);
+    rc = tc::make_tmap(&tb, B, (long long)batch * N, K, ldb, BN);
     if (rc != LPD_OK) return rc;
     tc::Params p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = scale; p.shift = shift;
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
-    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0;
+    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = 0;
+    p.bM = batch > 1 ? M : 0; p.bN = batch > 1 ? N : 0; p.accumulate = accumulate ? 1 : 0;
     cudaStream_t st = as_stream(stream);
     if (BN == 64) return tc::launch<64, 8>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6>(ta, tb, p, st);
     return tc::launch<256, 4>(ta, tb, p, st);
+}
+
+extern "C" int lpd_gemm_tf32(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                             int M, int N, int K, const float* scale, const float* shift, int act, float slope,
+                             void* stream) {
+    return lpd_gemm_tf32_ex(A, lda, B, ldb, C, ldc, M, N, K, 1, 0, scale, shift, act, slope, stream);
 }
 
 extern "C" int lpd_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long strideC,
@@ -260,7 +274,7 @@ extern "C" int lpd_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb
     if (rc != LPD_OK) return rc;
     tc::Params p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = nullptr; p.shift = nullptr; p.neg_slope = 1.f;
-    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = strideC;
+    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = strideC; p.bM = p.bN = 0; p.accumulate = 0;
     cudaStream_t st = as_stream(stream);
     if (BN == 64) return tc::launch<64, 8, true>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6, true>(ta, tb, p, st);

@@ -189,18 +189,24 @@ def get_precision() -> str:
     return _precision
 
 
-def gemm_tf32(A, W, *, M, N, K, lda=None, out=None, ldc=None, scale=None, shift=None, act=ACT_NONE, slope=0.0):
-    """out[m][n] = act(scale[n] * sum_k A[m][k] W[n][k] + shift[n]) on the tensor cores (TF32)."""
+def gemm_tf32(A, W, *, M, N, K, lda=None, ldw=None, out=None, ldc=None, scale=None, shift=None, act=ACT_NONE, slope=0.0, batch=1,
+              accumulate=False):
+    """out[z*M + m][n] (+)= act(scale[n] * sum_k A[z*M + m][k] W[z*N + n][k] + shift[n]) on the tensor cores (TF32);
+    batch > 1: the per-slice matrices are stacked on their row axis; accumulate: adds into `out`."""
     lib = _lib.load()
     _f32(A, "A"), _f32(W, "W")
     lda = K if lda is None else lda
+    ldw = K if ldw is None else ldw
     if out is None:
-        out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+        if accumulate:
+            raise ValueError("gemm_tf32: accumulate needs an output buffer")
+        out = torch.empty(batch * M, N, device=A.device, dtype=torch.float32)
         ldc = N
     elif ldc is None:
         ldc = out.stride(-2)
-    _call(f"lpd_gemm_tf32[{M}x{N}x{K}]", 1, lib.lpd_gemm_tf32, A.data_ptr(), lda, W.data_ptr(), K, out.data_ptr(), ldc,
-          M, N, K, _p(scale), _p(shift), act, float(slope), _stream())
+    label = f"lpd_gemm_tf32[{M}x{N}x{K}]" if batch == 1 else f"lpd_gemm_tf32[{M}x{N}x{K}x{batch}]"
+    _call(label, 1, lib.lpd_gemm_tf32_ex, A.data_ptr(), lda, W.data_ptr(), ldw, out.data_ptr(), ldc,
+          M, N, K, batch, int(bool(accumulate)), _p(scale), _p(shift), act, float(slope), _stream())
     return out
 
 

@@ -25,11 +25,11 @@ A_MK, A_KM, B_NK, B_KN = ops.A_MK, ops.A_KM, ops.B_NK, ops.B_KN
 def dgrad(dz, lddz, w, rows, N, K, out=None, ldc=None, accumulate=False, tf32_ok=True):
     """da[r][k] (+)= sum_n dz[r][n] * w[n][k]   (input gradient of z = a . w^T, w [N, K]).
     In "tf32" precision mode the product runs on the tensor cores against a transposed copy of the (small) weight."""
-    if (tf32_ok and not accumulate and ops.get_precision() == "tf32" and N >= 32 and N % 4 == 0 and lddz % 4 == 0 and K >= 64
+    if (tf32_ok and ops.get_precision() == "tf32" and N >= 32 and N % 4 == 0 and lddz % 4 == 0 and K >= 64
             and K % 4 == 0 and rows >= 128 and (ldc is None or ldc % 4 == 0) and dz.data_ptr() % 16 == 0
             and (out is None or out.data_ptr() % 16 == 0)):
         wt = ops.transpose(w.unsqueeze(0))[0]                                   # [K, N]
-        return ops.gemm_tf32(dz, wt, M=rows, N=K, K=N, lda=lddz, out=out, ldc=ldc)
+        return ops.gemm_tf32(dz, wt, M=rows, N=K, K=N, lda=lddz, out=out, ldc=ldc, accumulate=accumulate)
     return ops.gemm(dz, w, a_layout=A_MK, b_layout=B_KN, M=rows, N=K, K=N, lda=lddz, ldb=K, out=out, ldc=ldc,
                     act=ops.ACT_ADD if accumulate else ops.ACT_NONE, aux=out if accumulate else None)
 
@@ -589,9 +589,15 @@ class NetVLADTrain:
         grads.add(nv.cluster_weights2, dwc2)
         f, a = self.f, self.a
         # vraw[b] = f[b]^T a[b]:  da[b] = f[b] . dvraw[b] ;  df[b] = a[b] . dvraw[b]^T (accumulated below)
-        da = ops.gemm(f, dvraw, a_layout=A_MK, b_layout=B_KN, M=N, N=K, K=D, lda=D, ldb=K, batch=B,
-                      strideA=N * D, strideB=D * K, strideC=N * K,
-                      out=torch.empty(M, K, device=f.device, dtype=torch.float32), ldc=K)
+        tc_ok = ops.get_precision() == "tf32" and N >= 128 and D % 4 == 0
+        if tc_ok:
+            dvraw_t = ops.transpose(dvraw.view(B, D, K))                            # [B, K, D]: K-contiguous weight slices
+            da = ops.gemm_tf32(f, dvraw_t, M=N, N=K, K=D, lda=D, batch=B,
+                               out=torch.empty(M, K, device=f.device, dtype=torch.float32), ldc=K)
+        else:
+            da = ops.gemm(f, dvraw, a_layout=A_MK, b_layout=B_KN, M=N, N=K, K=D, lda=D, ldb=K, batch=B,
+                          strideA=N * D, strideB=D * K, strideC=N * K,
+                          out=torch.empty(M, K, device=f.device, dtype=torch.float32), ldc=K)
         ds = ops.softmax64_bwd(da, a, dasum, M, N)
         dapre = self.bn_a.bwd(ds, K, grads)
         wc = nv.cluster_weights.detach()
@@ -602,8 +608,11 @@ class NetVLADTrain:
             ops.gemm_tf32(dapre, wc, M=M, N=D, K=K, lda=K, out=df, ldc=D)           # Wc [D][K] is already K-contiguous
         else:
             ops.gemm(dapre, wc, a_layout=A_MK, b_layout=B_NK, M=M, N=D, K=K, lda=K, ldb=K, out=df, ldc=D)
-        ops.gemm(a, dvraw, a_layout=A_MK, b_layout=B_NK, M=N, N=D, K=K, lda=K, ldb=K, batch=B,
-                 strideA=N * K, strideB=D * K, strideC=N * D, out=df, ldc=D, act=ops.ACT_ADD, aux=df)
+        if tc_ok:
+            ops.gemm_tf32(a, dvraw, M=N, N=D, K=K, lda=K, batch=B, out=df, ldc=D, accumulate=True)
+        else:
+            ops.gemm(a, dvraw, a_layout=A_MK, b_layout=B_NK, M=N, N=D, K=K, lda=K, ldb=K, batch=B,
+                     strideA=N * K, strideB=D * K, strideC=N * D, out=df, ldc=D, act=ops.ACT_ADD, aux=df)
         return df
 
 

@@ -289,6 +289,25 @@ def test_gemm_tf32_tensor_core_path(cuda, M, N, K, ldx):
     assert np.abs(strict.cpu().numpy() - got[:, 32:32 + N]).max() < 2.0 ** -9 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("M,N,K,batch,accumulate", [(4096, 64, 1024, 3, False), (1024, 1024, 64, 4, True), (300, 200, 96, 2, True),
+                                                     (128, 128, 512, 1, True), (640, 72, 40, 5, False)])
+def test_gemm_tf32_batched_and_accumulating(cuda, M, N, K, batch, accumulate):
+    """lpd_gemm_tf32_ex: row-stacked slices, optional C += ... (NetVLAD backward products, accumulating input gradients);
+    slices whose M / N are not tile multiples must not leak into their neighbours."""
+    r = rng(M + N + K + batch)
+    A = r.standard_normal((batch * M, K)).astype(np.float32)
+    W = (r.standard_normal((batch * N, K)) / np.sqrt(K)).astype(np.float32)
+    C0 = r.standard_normal((batch * M, N)).astype(np.float32)
+    out = dev(C0.copy())
+    ops.gemm_tf32(dev(A), dev(W), M=M, N=N, K=K, batch=batch, out=out, ldc=N, accumulate=accumulate)
+    got = out.cpu().numpy()
+    for z in range(batch):
+        ref = A[z * M:(z + 1) * M].astype(np.float64) @ W[z * N:(z + 1) * N].astype(np.float64).T
+        if accumulate:
+            ref = ref + C0[z * M:(z + 1) * M]
+        assert np.abs(got[z * M:(z + 1) * M] - ref).max() < 2.0 ** -9 * max(np.abs(ref).max(), 1.0), f"slice {z}"
+
+
 @pytest.mark.parametrize("M,N,K,batch,lda,ldb", [(1024, 64, 4096, 3, 1024, 64), (128, 128, 704, 5, 128, 128), (256, 64, 1000, 1, 256, 64),
                                                   (1024, 512, 2048, 2, 1024, 512), (200, 72, 320, 2, 264, 80), (512, 128, 96, 4, 512, 512)])
 def test_gemm_tf32_tn_rows_contraction(cuda, M, N, K, batch, lda, ldb):
