@@ -279,7 +279,7 @@ def run_ours(args):
     # ---- end to end through the public API: pinned host clouds -> descriptors in host memory ----
     big = torch.cat([h[:, 0] for h in host], 0)                      # [4*64, N, 3] host
     reps = max(1, (args.steps + n_rot - 1) // n_rot)
-    evaluate.get_latent_vectors(model, big[:BATCH].pin_memory(), batch_num=BATCH)   # warm
+    evaluate.get_latent_vectors(model, big, batch_num=BATCH)   # warm (captures the driver's CUDA graph of a full batch)
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()

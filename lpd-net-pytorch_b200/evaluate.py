@@ -67,10 +67,49 @@ def get_recall(m, n, DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS):
     return recall, top1_similarity_score, one_percent_recall
 
 
-def get_latent_vectors(model, clouds, batch_num: int = 64, pin: bool = True) -> np.ndarray:
+class _EmbedGraph:
+    """One CUDA graph of `model(x)` for a fixed [batch, 1, N, 3] input (eval mode): the ~25 kernel launches of a step
+    replay without any host-side issue cost.  Invalidated when a parameter / buffer of the model changes."""
+
+    def __init__(self, model, shape, dev):
+        self.key = self._key(model)
+        self.shape = tuple(shape)
+        self.x = torch.zeros(shape, device=dev, dtype=torch.float32)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                      # warm-up outside the capture: weight folding, smem opt-ins, allocator
+                model(self.x)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.y = model(self.x)
+
+    @staticmethod
+    def _key(model):
+        return tuple((t.data_ptr(), t._version) for t in list(model.parameters()) + list(model.buffers()))
+
+    def valid_for(self, model, shape):
+        return self.shape == tuple(shape) and self.key == self._key(model)
+
+
+class _Staging:
+    """Two-slot staging ring of the embedding driver, cached on the model: pinned host buffers (cudaHostAlloc per batch was
+    the dominant and most erratic cost of the end-to-end path) and their device twins."""
+
+    def __init__(self, shape, dev):
+        self.shape = tuple(shape)
+        self.host = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self.dev = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.copied = [None, None]      # H2D copy of the slot finished (copy stream)
+        self.consumed = [None, None]    # compute stream has read the slot's device buffer
+
+
+def get_latent_vectors(model, clouds, batch_num: int = 64, pin: bool = True, use_graph: bool = True) -> np.ndarray:
     """Eval-mode embedding of `clouds` ([n, N, 3] numpy / tensor, host memory) in batches of `batch_num`
     (reference :96-159: batch = eval_batch_size * (1 + P + Nn), tail batch handled, model.eval()/train() toggled).
-    Host->device copies are issued from pinned memory on a side stream so they overlap the previous batch."""
+    Batches go through a two-slot pinned staging ring and a side copy stream, so the host->device copy of batch i+1
+    overlaps the kernels of batch i; full batches replay one captured CUDA graph (the ragged tail runs eagerly)."""
     was_training = model.training
     model.eval()
     dev = _device()
@@ -81,30 +120,62 @@ def get_latent_vectors(model, clouds, batch_num: int = 64, pin: bool = True) -> 
     n = x.shape[0]
     out = torch.empty(n, model.net_vlad.output_dim if hasattr(model, "net_vlad") else 256, dtype=torch.float32,
                       pin_memory=pin)
+    if n == 0:
+        model.train(was_training)
+        return out.numpy()
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
-    staged = None
+    shape = (batch_num,) + tuple(x.shape[1:])
 
-    def stage(lo):
+    st = getattr(model, "_lpd_staging", None)
+    if st is None or st.shape != shape or st.dev[0].device != dev:
+        st = _Staging(shape, dev)
+        model._lpd_staging = st
+    graph = None
+    if use_graph and n >= 3 * batch_num:
+        graph = getattr(model, "_lpd_embed_graph", None)
+        if graph is None or not graph.valid_for(model, shape):
+            graph = _EmbedGraph(model, shape, dev)
+            model._lpd_embed_graph = graph
+
+    def stage(lo, slot):
         hi = min(n, lo + batch_num)
-        src = x[lo:hi].pin_memory() if pin and not x.is_pinned() else x[lo:hi]
+        cnt = hi - lo
+        if st.copied[slot] is not None:
+            st.copied[slot].synchronize()                     # the pinned slot is free again (its last H2D copy is done)
+        src = x[lo:hi]
+        if not (pin and x.is_pinned()):
+            st.host[slot][:cnt].copy_(src)                    # pageable -> pinned (host memcpy)
+            src = st.host[slot][:cnt]
         with torch.cuda.stream(copy_stream):
-            d = src.to(dev, non_blocking=True)
+            if st.consumed[slot] is not None:
+                copy_stream.wait_event(st.consumed[slot])     # the device slot has been read by the compute stream
+            st.dev[slot][:cnt].copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return lo, hi, d, ev, src
+        st.copied[slot] = ev
+        return lo, hi, slot
 
     with torch.no_grad():
-        if n:
-            staged = stage(0)
+        staged = stage(0, 0)
         while staged is not None:
-            lo, hi, d, ev, _keep = staged
-            staged = stage(hi) if hi < n else None
-            main.wait_event(ev)
-            d.record_stream(main)
-            o = model(d)
+            lo, hi, slot = staged
+            staged = stage(hi, slot ^ 1) if hi < n else None
+            main.wait_event(st.copied[slot])
+            d = st.dev[slot][:hi - lo]
+            if graph is not None and hi - lo == batch_num:
+                graph.x.copy_(d, non_blocking=True)           # device-to-device into the graph's static input
+                graph.graph.replay()
+                o = graph.y
+            else:
+                o = model(d)
+            done = torch.cuda.Event()
+            done.record(main)
+            st.consumed[slot] = done
             out[lo:hi].copy_(o, non_blocking=True)
     torch.cuda.synchronize(dev)
+    st.copied = [None, None]
+    st.consumed = [None, None]
     model.train(was_training)
     return out.numpy()
 

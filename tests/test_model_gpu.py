@@ -159,6 +159,26 @@ def test_get_latent_vectors_batches_and_tail(cuda, golden):
     assert not model.training
 
 
+def test_get_latent_vectors_graph_replay_matches_eager_and_tracks_weights(cuda, golden):
+    """full batches replay a captured CUDA graph: same bits as the eager call, re-captured when a weight changes"""
+    g = golden("c2_lpdnet_eval_small")
+    model, _ = build(g, num_points=1024, emb_dims=1024, featnet="lpdnet")
+    x = synth.clouds(11, 1024, seed=9)
+    with torch.no_grad():
+        want = model(x.cuda()).cpu().numpy()
+    got = evaluate.get_latent_vectors(model, x[:, 0].numpy(), batch_num=3)          # 3 graph replays + eager tail of 2
+    assert hasattr(model, "_lpd_embed_graph") and np.array_equal(got, want)
+    again = evaluate.get_latent_vectors(model, x[:, 0].numpy(), batch_num=3)        # cached graph
+    assert np.array_equal(again, want)
+    eager = evaluate.get_latent_vectors(model, x[:, 0].numpy(), batch_num=3, use_graph=False)
+    assert np.array_equal(eager, want)
+    with torch.no_grad():
+        model.net_vlad.cluster_weights.mul_(1.5)                                    # in-place update: the graph is stale
+        want2 = model(x.cuda()).cpu().numpy()
+    got2 = evaluate.get_latent_vectors(model, x[:, 0].numpy(), batch_num=3)
+    assert np.array_equal(got2, want2) and not np.array_equal(want2, want)
+
+
 # ------------------------------------------------------------------------------------------------ TF32 (tensor-core) mode
 TF32_TOL = 2e-4   # stated looser bound for the tcgen05 kind::tf32 path (north_star allows one); measured values are printed
 
