@@ -11,6 +11,7 @@
 namespace lpd {
 
 constexpr int TR_THREADS = 256;
+constexpr int EDGE_U = 5;         // neighbour rows gathered per thread before any of them is consumed (k = 20: four rounds)
 
 // d act(v) / d v for the activations that follow a BatchNorm on the path.  GATE: out = aux * sigmoid(v).
 __device__ __forceinline__ float act_grad(float v, int act, float slope, float aux) {
@@ -239,16 +240,28 @@ edge_sel_stats_kernel(EdgeArgs a, const float* __restrict__ gamma, float* __rest
             int bi[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int u = 0; u < 4; ++u) best[u] = gm[u] >= 0.f ? -INFINITY : INFINITY;
-            for (int m = 0; m < a.k; ++m) {
-                const int j = __ldg(ip + m);
-                const float4 v4 = __ldg(reinterpret_cast<const float4*>(a.p + (cloud0 + j) * a.ldp + c));
-                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            // EDGE_U neighbour rows in flight per thread (the index -> row dependency chain was the whole cost of this loop);
+            // the accumulation order stays m ascending
+            for (int m0 = 0; m0 < a.k; m0 += EDGE_U) {
+                int jj[EDGE_U];
+                float4 vv[EDGE_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const bool better = gm[u] >= 0.f ? (v[u] > best[u]) : (v[u] < best[u]);
-                    if (better) { best[u] = v[u]; bi[u] = m; }
-                    sum[u] += v[u];
-                    sq[u] = fmaf(v[u], v[u], sq[u]);
+                for (int w = 0; w < EDGE_U; ++w) jj[w] = (m0 + w < a.k) ? __ldg(ip + m0 + w) : 0;
+#pragma unroll
+                for (int w = 0; w < EDGE_U; ++w) vv[w] = __ldg(reinterpret_cast<const float4*>(a.p + (cloud0 + jj[w]) * a.ldp + c));
+#pragma unroll
+                for (int w = 0; w < EDGE_U; ++w) {
+                    const int m = m0 + w;
+                    if (m < a.k) {
+                        const float v[4] = {vv[w].x, vv[w].y, vv[w].z, vv[w].w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool better = gm[u] >= 0.f ? (v[u] > best[u]) : (v[u] < best[u]);
+                            if (better) { best[u] = v[u]; bi[u] = m; }
+                            sum[u] += v[u];
+                            sq[u] = fmaf(v[u], v[u], sq[u]);
+                        }
+                    }
                 }
             }
             float qv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -397,27 +410,40 @@ edge_bwd_kernel(EdgeArgs a, const float* __restrict__ bn, int act, float slope,
                 ar[0] = a4.x; ar[1] = a4.y; ar[2] = a4.z; ar[3] = a4.w;
             }
             float dqa[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int m = 0; m < a.k; ++m) {
-                const int j = __ldg(ip + m);
-                const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.p + (cloud0 + j) * a.ldp + c));
-                const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-                float dyv[4] = {0.f, 0.f, 0.f, 0.f};
-                if (dy) { const float4 t = __ldg(reinterpret_cast<const float4*>(dy + (pt * a.k + m) * C + c)); dyv[0] = t.x; dyv[1] = t.y; dyv[2] = t.z; dyv[3] = t.w; }
-                float o[4];
+            for (int m0 = 0; m0 < a.k; m0 += EDGE_U) {      // EDGE_U rows in flight, accumulation order unchanged (see above)
+                int jj[EDGE_U];
+                float4 pp[EDGE_U], dd[EDGE_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float zz = pv[u] + qv[u];
-                    const float d = (dyv[u] + (m == ar[u] ? dxv[u] : 0.f)) * act_grad(fmaf(sc[u], zz, sh[u]), act, slope, 0.f);
-                    const float xh = (zz - mu[u]) * is[u];
-                    if (APPLY) {
-                        o[u] = sc[u] * (d - k1[u] - xh * k2[u]);
-                        dqa[u] += o[u];
-                    } else {
-                        s1[u] += d;
-                        s2[u] += (double)d * xh;
+                for (int w = 0; w < EDGE_U; ++w) jj[w] = (m0 + w < a.k) ? __ldg(ip + m0 + w) : 0;
+#pragma unroll
+                for (int w = 0; w < EDGE_U; ++w) {
+                    pp[w] = __ldg(reinterpret_cast<const float4*>(a.p + (cloud0 + jj[w]) * a.ldp + c));
+                    dd[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (dy && m0 + w < a.k) dd[w] = __ldg(reinterpret_cast<const float4*>(dy + (pt * a.k + m0 + w) * C + c));
+                }
+#pragma unroll
+                for (int w = 0; w < EDGE_U; ++w) {
+                    const int m = m0 + w;
+                    if (m < a.k) {
+                        const float pv[4] = {pp[w].x, pp[w].y, pp[w].z, pp[w].w};
+                        const float dyv[4] = {dd[w].x, dd[w].y, dd[w].z, dd[w].w};
+                        float o[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float zz = pv[u] + qv[u];
+                            const float d = (dyv[u] + (m == ar[u] ? dxv[u] : 0.f)) * act_grad(fmaf(sc[u], zz, sh[u]), act, slope, 0.f);
+                            const float xh = (zz - mu[u]) * is[u];
+                            if (APPLY) {
+                                o[u] = sc[u] * (d - k1[u] - xh * k2[u]);
+                                dqa[u] += o[u];
+                            } else {
+                                s1[u] += d;
+                                s2[u] += (double)d * xh;
+                            }
+                        }
+                        if (APPLY) atomicAdd(reinterpret_cast<float4*>(dp + (cloud0 + jj[w]) * lddp + c), make_float4(o[0], o[1], o[2], o[3]));
                     }
                 }
-                if (APPLY) atomicAdd(reinterpret_cast<float4*>(dp + (cloud0 + j) * lddp + c), make_float4(o[0], o[1], o[2], o[3]));
             }
             if (APPLY && dq) *reinterpret_cast<float4*>(dq + pt * lddq + c) = make_float4(dqa[0], dqa[1], dqa[2], dqa[3]);
         }
