@@ -89,16 +89,15 @@ def kernel_work(label: str, B: int):
 
 
 def make_roofline(top, tot, cnt, step_ms, peaks, B):
-    """roofline object of the dominant kernel family: algorithmic FLOPs (or bytes) of ONE launch / its CUDA-event time.  The
-    bound is the tensor pipe when the algorithmic intensity is above the ridge of the measured peaks, HBM otherwise."""
+    """roofline object of the dominant kernel family: algorithmic FLOPs (or bytes) of ONE launch / its CUDA-event time."""
     work = kernel_work(top, B)
     if work is None:
         return {"kernel": top, "bound": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": ncu_traffic(top),
                 "share_of_step": tot[top] / step_ms, "ms_per_launch": tot[top] / cnt[top], "note": "no algorithmic work model for this kernel"}
     flops, byts = work
     per_launch_ms = tot[top] / cnt[top]
-    ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-    if flops > 0 and flops / byts >= ridge:
+    # dense contractions (>= 16 FLOP per compulsory byte) are graded on the tensor pipe, streaming kernels on HBM
+    if flops > 0 and flops / byts >= 16.0:
         tf = flops / (per_launch_ms * 1e-3) / 1e12
         return {"kernel": top, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": tf / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(top),
