@@ -50,7 +50,9 @@ class Prepared:
 
 
 def training_unsupported(module: nn.Module, what: str):
+    """Sub-modules called on their own support eval mode only; train mode (batch-statistics BatchNorm + the hand-written
+    backward) is entered through PointNetVlad.forward (lpdnet_b200/train.py)."""
     if module.training:
         raise LpdError(
-            f"{what}: train() mode (batch-statistics BatchNorm + backward) is not built yet in this round; "
-            f"call .eval() — the eval-mode embedding path is the supported hot path")
+            f"{what}: called directly in train() mode; the training path (batch-statistics BatchNorm + backward) runs "
+            f"through PointNetVlad.forward — call .eval() for a stand-alone forward of this sub-module")
