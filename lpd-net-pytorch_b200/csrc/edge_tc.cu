@@ -124,7 +124,7 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
             const int cj = nj;
             const float4 cq = nq;
             prefetch(t + tstep);
-            mbar_wait_sleep(&yempty[grp], ph ^ 1);
+            mbar_wait(&yempty[grp], ph ^ 1);
             for (int pl = pw; pl < PTS; pl += DG_GROUP_WARPS) {
                 const long long pt = t * PTS + pl;
                 if (pt >= P.total_pts) break;
@@ -175,8 +175,8 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
             if (issuer) {   // warp-uniform: the whole warp runs the issue sequence, elect.sync picks the lane (see tc_common.cuh)
                 // all six producer warps of the group run in lockstep on equal work, so this wait is short
                 if (!w_ready) { mbar_wait(wfull, 0); w_ready = true; }
-                mbar_wait_sleep(&tempty[grp], ph ^ 1);
-                mbar_wait_sleep(&yfull[grp], ph);
+                mbar_wait(&tempty[grp], ph ^ 1);
+                mbar_wait(&yfull[grp], ph);
                 tc_fence_after();
                 const uint32_t y_addr = smem_u32(y_s + grp * OP_BYTES);
 #pragma unroll
@@ -203,7 +203,7 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
         long long t = blockIdx.x;
         for (uint32_t it = 0; t < P.num_tiles; t += gridDim.x, ++it) {
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
-            mbar_wait_sleep(&tfull[s], ph);
+            mbar_wait(&tfull[s], ph);
             tc_fence_after();
             if (warp * 32 < P.C2) {
                 for (int pl = 0; pl < PTS; ++pl) {

@@ -103,6 +103,13 @@ class _Staging:
         self.dev = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
         self.copied = [None, None]      # H2D copy of the slot finished (copy stream)
         self.consumed = [None, None]    # compute stream has read the slot's device buffer
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.out_host = None            # pinned landing buffer of the descriptors (grown on demand, copied out on return)
+
+    def out(self, n, dim):
+        if self.out_host is None or self.out_host.shape[0] < n or self.out_host.shape[1] != dim:
+            self.out_host = torch.empty(max(n, 256), dim, dtype=torch.float32, pin_memory=True)
+        return self.out_host[:n]
 
 
 def get_latent_vectors(model, clouds, batch_num: int = 64, pin: bool = True, use_graph: bool = True) -> np.ndarray:
@@ -118,12 +125,10 @@ def get_latent_vectors(model, clouds, batch_num: int = 64, pin: bool = True, use
     if x.dim() == 3:
         x = x.unsqueeze(1)
     n = x.shape[0]
-    out = torch.empty(n, model.net_vlad.output_dim if hasattr(model, "net_vlad") else 256, dtype=torch.float32,
-                      pin_memory=pin)
+    dim = model.net_vlad.output_dim if hasattr(model, "net_vlad") else 256
     if n == 0:
         model.train(was_training)
-        return out.numpy()
-    copy_stream = torch.cuda.Stream(device=dev)
+        return np.empty((0, dim), dtype=np.float32)
     main = torch.cuda.current_stream(dev)
     shape = (batch_num,) + tuple(x.shape[1:])
 
@@ -131,6 +136,8 @@ def get_latent_vectors(model, clouds, batch_num: int = 64, pin: bool = True, use
     if st is None or st.shape != shape or st.dev[0].device != dev:
         st = _Staging(shape, dev)
         model._lpd_staging = st
+    copy_stream = st.copy_stream
+    out = st.out(n, dim)                                      # cudaHostAlloc per call would cost ~1 ms
     graph = None
     if use_graph and n >= 3 * batch_num:
         graph = getattr(model, "_lpd_embed_graph", None)
@@ -177,7 +184,7 @@ def get_latent_vectors(model, clouds, batch_num: int = 64, pin: bool = True, use
     st.copied = [None, None]
     st.consumed = [None, None]
     model.train(was_training)
-    return out.numpy()
+    return out.numpy().copy()                                 # the landing buffer is reused by the next call
 
 
 def evaluate_sets(DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS):
