@@ -96,11 +96,12 @@ int lpd_knn(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, 
 size_t lpd_knn_workspace_bytes(int B, int N, int C, int k);
 int lpd_knn_tc(const float* x, int B, int N, int C, int k, void* idx, int idx_i64,
                void* workspace, size_t workspace_bytes, void* stream);
-/* Filter formulation used by lpd_knn_tc (process-wide; returns the previous value, v outside 0..2 only queries):
+/* Filter formulation used by lpd_knn_tc (process-wide; returns the previous value, v outside 0..3 only queries):
  *   0  one pass, 3xTF32 gram, per-row replace-worst candidate lists (csrc/knn_tc.cu);
  *   1  two passes, fp16 gram of the centred features with the norm folded into the MMA, strided group maxima -> provable
  *      threshold -> collect, 128 query rows per work item (csrc/knn_tc2.cu; default);
- *   2  the same with 256 query rows per work item.
+ *   2  the same with 256 query rows per work item;
+ *   3  variant 1 with the query tile held in tensor memory (TS-mode tcgen05.mma; measured on par with 1).
  * The indices are bit-identical to lpd_knn for every variant. */
 int lpd_knn_tc_variant(int v);
 /* Diagnostics: byte offset, inside the workspace of the LAST lpd_knn_tc call with these sizes and the current variant, of

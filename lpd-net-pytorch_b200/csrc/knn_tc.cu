@@ -425,13 +425,13 @@ size_t knn2_flags_offset(int B, int N, int k);
 int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes, int mt,
              cudaStream_t st);
 // 0 = single-pass 3xTF32 replace-worst filter (this file); 1 / 2 = two-pass fp16 threshold filter (knn_tc2.cu) with
-// 128 / 256 query rows per work item.  Every variant returns the same (canonical) indices.
+// 128 / 256 query rows per work item; 3 = variant 1 with the query tile in tensor memory (TS-mode MMA).  Every variant returns the same (canonical) indices.
 static int g_knn_variant = 1;
 }}
 
 extern "C" int lpd_knn_tc_variant(int v) {
     const int prev = lpd::tc::g_knn_variant;
-    if (v >= 0 && v <= 2) lpd::tc::g_knn_variant = v;
+    if (v >= 0 && v <= 3) lpd::tc::g_knn_variant = v;
     return prev;
 }
 

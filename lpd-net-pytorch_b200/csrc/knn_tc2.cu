@@ -45,8 +45,10 @@
 //   the canonical chain itself (<= 19 ulp of the norms).
 //
 // What bounds it (ncu, B200, 64 clouds x 4096): the accumulators are read from TMEM at 64 B/clk/SM (4.3 GB in pass 1 alone
-// = 0.26 ms) and an SS-mode tcgen05.mma costs (128 + N)/4 clk of shared-memory operand reads on top of its N/2 clk of math,
-// which is why a stage is N = 128 wide; the single-thread roles issue through elect.sync (tc_common.cuh).
+// = 0.26 ms), and the MMA stream by itself (scan disabled) needs 0.31 ms: ~120 clk per 128 x 128 x 16 MMA, twice the
+// tensor-pipe floor, whether the query tile comes from shared memory or from tensor memory (TS variant below: no gain) and
+// whether consecutive MMAs share an accumulator or not.  N = 64 stages were worse (~90 clk per half-size MMA).  The
+// single-thread roles issue through elect.sync (tc_common.cuh).
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -67,6 +69,7 @@ constexpr int K2_TBL = 128;      // candidate stages per cloud the pass-2 skip t
 struct Knn2Params {
     const float* nrmpad;   // [B][Npad] centred squared norms, +inf padded   (storage order, like the operand rows)
     const float* snpad;    // [B][Npad] their square roots, 0 padded          (storage order)
+    const uint4* xh;       // [B*N][8] the fp16 operand rows (64 halves = 8 x 16 B), storage order (TS mode reads query rows)
     const uint4* ext;      // [B][Npad/64][128] K-extension rows of the candidate tiles (2 KB per tile, core-matrix layout)
     const float* xxpad;    // [B][Npad] canonical squared norms               (point order)
     const float* r2;       // [B] max canonical squared norm
@@ -128,6 +131,20 @@ __device__ __forceinline__ void mbar_expect_tx_p(uint64_t* bar, uint32_t bytes, 
         "elect.sync _|q, 0xffffffff;\n\t"
         "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
         ::"r"(smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
+}
+// the same with the A operand (query tile) in TENSOR MEMORY: lane = query row, 32-bit column c = fp16 elements (2c, 2c+1)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st4(uint32_t taddr, const uint4& v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // kind::f16 with fp16 operands (format 0), fp32 accumulate, A and B K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
@@ -356,16 +373,16 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return r;
 }
 
-template <int MT>
+template <int MT, bool TS = false>
 struct K2Smem {
     static constexpr int SCAN_THREADS = 256 * MT;
-    static constexpr int TSTAGES = K2_TCOLS / (K2_C * MT);
+    static constexpr int TSTAGES = TS ? 3 : K2_TCOLS / (K2_C * MT);   // TS: columns 384.. hold the two query buffers
     static constexpr int EXS = SCAN_THREADS + 1;          // exchange-buffer row stride (words)
     static constexpr uint32_t A_TILE = 128 * 128;         // one 128-row query tile: 64 fp16 = 128 B per row
     static constexpr uint32_t A_BYTES = MT * A_TILE;
     static constexpr uint32_t B_BYTES = K2_C * 128;
     static constexpr uint32_t BX_BYTES = K2_C * 32;       // K-extension of a candidate tile
-    static constexpr size_t off_b = 2 * A_BYTES;          // two query buffers (next item prefetched)
+    static constexpr size_t off_b = TS ? 0 : 2 * A_BYTES; // two query buffers (next item prefetched); none in TS mode
     static constexpr size_t off_bx = off_b + K2_BSTAGES * B_BYTES;
     static constexpr size_t off_ax = off_bx + K2_BSTAGES * BX_BYTES;         // constant query-side extension, 128 rows
     static constexpr size_t off_xs = off_ax + 128 * 32;
@@ -376,11 +393,13 @@ struct K2Smem {
     static_assert(total <= 227 * 1024, "knn2 shared memory budget");
 };
 
-template <int MT, int CAP, bool TIGHT>
+template <int MT, int CAP, bool TIGHT, bool TS>
 __global__ void __launch_bounds__(256 * MT + 64, 1)
 knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Knn2Params P) {
-    using S = K2Smem<MT>;
+    static_assert(!TS || MT == 1, "TS mode: one 128-row query tile per item");
+    using S = K2Smem<MT, TS>;
     constexpr int SCAN_WARPS = 8 * MT;
+    constexpr uint32_t ACOL = 384;                       // TS: TMEM column of query buffer 0 (buffer 1 at + 64)
     constexpr int TCOLS = K2_C * MT;                       // TMEM columns per accumulator stage
     constexpr int K2_TSTAGES = S::TSTAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -418,13 +437,13 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
-            for (int s = 0; s < 2; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&afull[s], TS ? SCAN_WARPS : 1); mbar_init(&aempty[s], 1); }
             for (int s = 0; s < K2_BSTAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
             for (int s = 0; s < K2_TSTAGES; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], SCAN_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS * K2_TSTAGES) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TS ? 512 : TCOLS * K2_TSTAGES) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -440,11 +459,13 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++icount) {
                 const int b = item / P.qtiles, q0 = (item % P.qtiles) * (128 * MT);
                 const uint32_t ab = icount & 1, aph = (icount >> 1) & 1;
-                mbar_wait_sleep(&aempty[ab], aph ^ 1);
-                mbar_expect_tx_p(&afull[ab], S::A_BYTES, leader);
+                if (!TS) {
+                    mbar_wait_sleep(&aempty[ab], aph ^ 1);
+                    mbar_expect_tx_p(&afull[ab], S::A_BYTES, leader);
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-                    tma_load_2d_p(a_s + ab * S::A_BYTES + mt * S::A_TILE, &tmap_a, &afull[ab], 0, b * P.N + q0 + mt * 128, leader);
+                    for (int mt = 0; mt < MT; ++mt)
+                        tma_load_2d_p(a_s + ab * S::A_BYTES + mt * S::A_TILE, &tmap_a, &afull[ab], 0, b * P.N + q0 + mt * 128, leader);
+                }
                 const uint4* extb = P.ext + (size_t)b * (P.Npad >> 6) * 128;
                 const float* snb = P.snpad + (size_t)b * P.Npad;
                 uint32_t s = tcount % K2_BSTAGES, ph = (tcount / K2_BSTAGES) & 1, xsl = tcount % K2_XSLOTS;
@@ -470,7 +491,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++icount) {
                 const uint32_t ab = icount & 1, aph = (icount >> 1) & 1;
                 mbar_wait_sleep(&afull[ab], aph);
+                if (TS) tc_fence_after();
                 const uint64_t da0 = make_smem_desc(smem_u32(a_s + ab * S::A_BYTES));
+                const uint32_t ta0 = tmem_base + ACOL + ab * 64;        // TS: query rows in tensor memory
                 uint32_t s = tcount % K2_BSTAGES, ph = (tcount / K2_BSTAGES) & 1;
                 uint32_t ts = tcount % K2_TSTAGES, tph = (tcount / K2_TSTAGES) & 1;
                 for (int cs = 0; cs < nstages; ++cs, ++tcount) {
@@ -479,14 +502,24 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tc_fence_after();
                     const uint64_t db = make_smem_desc(smem_u32(b_s + s * S::B_BYTES));
                     const uint64_t dbx = make_smem_desc_ext(smem_u32(bx_s + s * S::BX_BYTES));
+                    if (TS) {                               // A from tensor memory: 8 columns (16 fp16) per K step, extension at + 32
+                        const uint32_t d = tmem_base + ts * TCOLS;
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint64_t da = da0 + (uint64_t)(mt * (S::A_TILE >> 4));
-                        const uint32_t d = tmem_base + ts * TCOLS + mt * K2_C;
+                        for (int ks = 0; ks < 4; ++ks) tc_mma_f16_ts(d, ta0 + ks * 8, db + (uint64_t)(ks * 2), idesc, ks ? 1u : 0u);
+                        tc_mma_f16_ts(d, ta0 + 32, dbx, idesc, 1u);
+                    } else {
+                        // K = 64 = 4 x 16 (32 bytes per step inside the 128-byte swizzle atom) + the K-extension, which subtracts
+                        // sigma^2 nrm_j / 2 and buries the padding; the query tiles of an item alternate (independent accumulators)
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)      // K = 64 = 4 x 16, 32 bytes per step inside the 128-byte swizzle atom
-                            tc_mma_f16_p(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, ks ? 1u : 0u, leader);
-                        tc_mma_f16_p(d, dax, dbx, idesc, 1u, leader);   // K-extension: subtracts sigma^2 nrm_j / 2 (and buries the padding)
+                        for (int ks = 0; ks < 5; ++ks) {
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint64_t da = da0 + (uint64_t)(mt * (S::A_TILE >> 4));
+                                const uint32_t d = tmem_base + ts * TCOLS + mt * K2_C;
+                                if (ks < 4) tc_mma_f16_p(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, ks ? 1u : 0u, leader);
+                                else tc_mma_f16_p(d, dax, dbx, idesc, 1u, leader);
+                            }
+                        }
                     }
                     tc_commit_p(&bempty[s], leader);
                     tc_commit_p(&tfull[ts], leader);
@@ -505,9 +538,43 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // this thread's 64 columns: positions [32 half, 32 half + 32) of BOTH 64-blocks of a stage, so that group j of the thread
         // is "storage position 32 half + j of every block" (64 distinct groups per row for the 64 points of any one block)
         const uint32_t tm_lane = ((uint32_t)(quad * 32) << 16) + mt * K2_C + half * 32;
-        uint32_t tcount = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        uint32_t tcount = 0, icount = 0;
+        // TS mode: the scan threads themselves put the query tile into tensor memory (each thread its own row: half 0 the
+        // 32-bit columns 0..19, half 1 the columns 20..31 + the constant K-extension 32..39), one item ahead of the MMAs
+        uint4 aw[5];
+        auto load_a = [&](int it2) {
+            const int b2 = it2 / P.qtiles, q02 = (it2 % P.qtiles) * 128;
+            const long long grow = (long long)b2 * P.N + q02 + quad * 32 + lane;
+            const bool inb = grow < (long long)P.B * P.N;
+            const uint4* src = P.xh + grow * 8;
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            if (half == 0) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) aw[i] = inb ? __ldg(src + i) : zero;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) aw[i] = inb ? __ldg(src + 5 + i) : zero;
+                const __half2 h01 = __floats2half2_rn(64.f, 0.03125f), h23 = __floats2half2_rn(6.103515625e-05f, 32768.f);
+                aw[3] = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23), 0u, 0u);
+                aw[4] = zero;
+            }
+        };
+        auto store_a = [&](uint32_t n) {                               // n = ordinal of the item inside this CTA
+            const uint32_t buf = n & 1, use = n >> 1;
+            mbar_wait(&aempty[buf], (use & 1) ^ 1);                    // the MMAs of item n - 2 have finished with this buffer
+            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + ACOL + buf * 64 + half * 20;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) tc_st4(ta + 4 * i, aw[i]);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&afull[buf]);
+        };
+        if (TS && blockIdx.x < items) { load_a(blockIdx.x); store_a(0); }
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++icount) {
             const int b = item / P.qtiles, q0 = (item % P.qtiles) * (128 * MT);
+            const bool have_next = TS && item + (int)gridDim.x < items;
+            if (have_next) load_a(item + gridDim.x);                   // in flight during pass 1
             const int srow = q0 + mt * 128 + quad * 32 + lane;        // storage position of this thread's query
             int row = srow;                                            // ... and the point it holds
             if ((srow >> 6) < full_blocks) {
@@ -587,6 +654,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 thr = fmaxf(tau0 - 2.f * eps * inv_cb, -1.0e9f);             // padded candidates sit near -2e9
                 if (!(eps * inv_cb < INFINITY)) thr = __int_as_float(0x7fc00000);   // unusable bound: collect nothing, fall back
             }
+            if (have_next) store_a(icount + 1);
             // ---------------- pass 2: collect everything at or above the threshold ----------------
             const int dthr = __reduce_max_sync(kFull, fkey(live ? gself - thr : -INFINITY));
             int cnt = 0;
@@ -657,7 +725,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     if (warp == SCAN_WARPS + 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS * K2_TSTAGES) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS ? 512 : TCOLS * K2_TSTAGES) : "memory");
     }
 }
 
@@ -816,15 +884,15 @@ struct Knn2Ws {
 
 size_t knn2_workspace_bytes(int B, int N, int k) { return Knn2Ws(B, N, k).total; }
 
-template <int MT, int CAP, bool TIGHT>
+template <int MT, int CAP, bool TIGHT, bool TS = false>
 static int knn2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const Knn2Params& P, cudaStream_t st) {
-    const size_t smem = K2Smem<MT>::total;
-    LPD_CUDA_CHECK(allow_smem(knn2_tc_kernel<MT, CAP, TIGHT>, smem));
+    const size_t smem = K2Smem<MT, TS>::total;
+    LPD_CUDA_CHECK(allow_smem(knn2_tc_kernel<MT, CAP, TIGHT, TS>, smem));
     int dev = 0, sms = 0;
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int items = P.B * P.qtiles;
-    knn2_tc_kernel<MT, CAP, TIGHT><<<items < sms ? items : sms, 256 * MT + 64, smem, st>>>(ta, tb, P);
+    knn2_tc_kernel<MT, CAP, TIGHT, TS><<<items < sms ? items : sms, 256 * MT + 64, smem, st>>>(ta, tb, P);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }
@@ -857,13 +925,15 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     rc = make_tmap_f16(&tb, xh, (long long)B * N, K2_C);      // 128 candidates per stage
     if (rc != LPD_OK) return rc;
     Knn2Params P;
-    P.nrmpad = nrmpad; P.snpad = snpad; P.ext = reinterpret_cast<const uint4*>(ws + W.off_ext); P.xxpad = xxpad; P.r2 = r2; P.r2c = r2c; P.sc = sc;
+    P.nrmpad = nrmpad; P.snpad = snpad; P.ext = reinterpret_cast<const uint4*>(ws + W.off_ext); P.xh = reinterpret_cast<const uint4*>(xh); P.xxpad = xxpad; P.r2 = r2; P.r2c = r2c; P.sc = sc;
     P.cnt = reinterpret_cast<int*>(ws + W.off_cnt);
     P.cand = reinterpret_cast<int*>(ws + W.off_cand);
     P.B = B; P.N = N; P.Npad = W.npad; P.k = k;
-    P.qtiles = ceil_div(N, 128 * mt); P.ctiles = ceil_div(N, K2_C);
+    P.qtiles = ceil_div(N, mt == 2 ? 256 : 128); P.ctiles = ceil_div(N, K2_C);
     // k <= 24: 40 slots per (row, half), uniform error bound; k <= 32: 64 slots, per-candidate bound
-    if (W.cap == 40) rc = (mt == 2) ? knn2_launch<2, 40, false>(ta, tb, P, st) : knn2_launch<1, 40, false>(ta, tb, P, st);
+    if (mt == 3) {          // 128 rows per item, query tile in tensor memory (TS-mode MMA)
+        rc = (W.cap == 40) ? knn2_launch<1, 40, false, true>(ta, tb, P, st) : knn2_launch<1, 64, true, true>(ta, tb, P, st);
+    } else if (W.cap == 40) rc = (mt == 2) ? knn2_launch<2, 40, false>(ta, tb, P, st) : knn2_launch<1, 40, false>(ta, tb, P, st);
     else             rc = (mt == 2) ? knn2_launch<2, 64, true>(ta, tb, P, st) : knn2_launch<1, 64, true>(ta, tb, P, st);
     if (rc != LPD_OK) return rc;
     rc = (W.cap == 40) ? knn2_refine_launch<40>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, st)
