@@ -1,16 +1,21 @@
 """Drop-in for the hot-path part of the reference's train_pointnetvlad.py: run_model (:202-217, the tuple layout contract)
 and the body of one training iteration (:121-130 / :150-159: zero_grad, run_model, loss, backward, optimizer.step).
-The epoch loop, logging, checkpoint naming and the DataLoaders around it are control plane and stay with the caller.
+Plus the checkpoint format and the learning-rate policy the reference wraps around it: save_model
+(:172-199), the two load paths (:64-76) and ReduceLROnPlateau (:92).  The epoch loop, logging and the DataLoaders are control
+plane and stay with the caller.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
 from .loss import pointnetvlad_loss as PNV_loss
 
-__all__ = ["run_model", "train_step", "FEATURE_OUTPUT_DIM"]
+__all__ = ["run_model", "train_step", "save_model", "load_checkpoint", "make_scheduler", "FEATURE_OUTPUT_DIM", "MODEL_FILENAME"]
 
 FEATURE_OUTPUT_DIM = 256  # reference config.py
+MODEL_FILENAME = "model.ckpt"  # reference config.py:8
 
 
 def run_model(model, queries, positives, negatives, other_neg, require_grad=True, num_points=None,
@@ -45,3 +50,47 @@ def train_step(model, optimizer, queries, positives, negatives, other_neg, margi
     loss.backward()
     optimizer.step()
     return loss.detach()
+
+
+def save_model(model, optimizer, epoch, total_iterations, ave_one_percent_recall, model_save_path, best_so_far=None,
+               filename=MODEL_FILENAME):
+    """Reference :172-199.  Writes `<path>/<epoch>-model.ckpt` = {'epoch','iter','state_dict','optimizer','recall'} (the
+    DataParallel wrapper, if any, is unwrapped) and, when the recall beats `best_so_far`, `<path>/best-model.ckpt`.
+    Returns the updated best recall (the reference keeps it in a module global)."""
+    model_to_save = model.module if isinstance(model, torch.nn.DataParallel) else model
+    payload = {
+        'epoch': epoch,
+        'iter': total_iterations,
+        'state_dict': model_to_save.state_dict(),
+        'optimizer': optimizer.state_dict(),
+        'recall': ave_one_percent_recall,
+    }
+    os.makedirs(model_save_path, exist_ok=True)
+    torch.save(payload, os.path.join(model_save_path, str(epoch) + "-" + filename))
+    best = -float("inf") if best_so_far is None else best_so_far
+    if best < ave_one_percent_recall:
+        best = ave_one_percent_recall
+        torch.save(payload, os.path.join(model_save_path, "best" + "-" + filename))
+    return best
+
+
+def load_checkpoint(model, optimizer, pretrained_path, map_location=None):
+    """Reference :64-76.  A path ending in '7' (`*.t7`) holds a bare state_dict and loads with strict=False; anything else
+    is the dict written by save_model: strict load of 'state_dict', optimizer state restored.  Returns
+    (starting_epoch, total_iterations); (0, 0) when the file does not exist or is a bare state_dict."""
+    if not os.path.exists(pretrained_path):
+        return 0, 0
+    if pretrained_path[-1] == "7":
+        model.load_state_dict(torch.load(pretrained_path, map_location=map_location), strict=False)
+        return 0, 0
+    checkpoint = torch.load(pretrained_path, map_location=map_location, weights_only=False)
+    model.load_state_dict(checkpoint['state_dict'], strict=True)
+    if optimizer is not None:
+        optimizer.load_state_dict(checkpoint['optimizer'])
+    return checkpoint['epoch'] + 1, checkpoint['iter']
+
+
+def make_scheduler(optimizer):
+    """Reference :92 (its `verbose=True` no longer exists in current torch): lr x 0.2 when the evaluation recall has not
+    improved by 0.1 (relative) for 2 epochs, floor 1e-5; stepped with `scheduler.step(ave_one_percent_recall)`."""
+    return torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, 'max', factor=0.2, patience=2, threshold=0.1, min_lr=0.00001)

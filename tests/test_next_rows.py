@@ -67,3 +67,33 @@ def test_feature_representation_and_update_vectors(cuda):
     vecs = data.update_vectors(model, clouds, batch_num=2)      # ragged tail batch
     assert model.training and vecs.shape == (5, 256) and data.TRAINING_LATENT_VECTORS is vecs
     assert np.abs(vecs - want).max() < 1e-5
+
+
+def test_checkpoint_format_and_scheduler(tmp_path):
+    """reference train_pointnetvlad.py:64-76,92,172-199: checkpoint dict keys, best-copy rule, both load paths, LR policy
+    (host logic; a CPU model is enough: the modules construct and (de)serialise without a device)"""
+    from lpdnet_b200 import train_pointnetvlad as tp
+    from lpdnet_b200.util.PointNetVlad import PointNetVlad
+    model = PointNetVlad(num_points=256, featnet="lpdnetorigin", emb_dims=128)
+    opt = torch.optim.Adam(model.parameters(), 1e-3)
+    best = tp.save_model(model, opt, 3, 1234, 71.5, str(tmp_path))
+    assert best == 71.5 and (tmp_path / "3-model.ckpt").exists() and (tmp_path / "best-model.ckpt").exists()
+    best = tp.save_model(model, opt, 4, 2000, 60.0, str(tmp_path), best_so_far=best)
+    ck = torch.load(tmp_path / "best-model.ckpt", weights_only=False)
+    assert best == 71.5 and ck["epoch"] == 3                                   # a worse epoch does not replace the best copy
+    assert set(ck) == {"epoch", "iter", "state_dict", "optimizer", "recall"}
+    other = PointNetVlad(num_points=256, featnet="lpdnetorigin", emb_dims=128)
+    opt2 = torch.optim.Adam(other.parameters(), 5e-4)
+    assert tp.load_checkpoint(other, opt2, str(tmp_path / "4-model.ckpt")) == (5, 2000)
+    for (ka, va), (kb, vb) in zip(model.state_dict().items(), other.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    assert opt2.param_groups[0]["lr"] == 1e-3
+    torch.save(model.state_dict(), tmp_path / "weights.t7")                    # bare state_dict path (strict=False)
+    third = PointNetVlad(num_points=256, featnet="lpdnetorigin", emb_dims=128)
+    assert tp.load_checkpoint(third, None, str(tmp_path / "weights.t7")) == (0, 0)
+    assert torch.equal(third.net_vlad.cluster_weights, model.net_vlad.cluster_weights)
+    assert tp.load_checkpoint(third, None, str(tmp_path / "missing.ckpt")) == (0, 0)
+    sched = tp.make_scheduler(opt)
+    for recall in (50.0, 50.0, 50.0, 50.0):                                    # no improvement for > patience epochs
+        sched.step(recall)
+    assert abs(opt.param_groups[0]["lr"] - 2e-4) < 1e-12
