@@ -151,6 +151,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int c = half * CPW + i;
                 const int col0 = n0 + c * 32;
                 if (col0 >= p.N || row0 >= p.M) break;  // warp-uniform: the rest is out of range
+                // accumulate mode: the old C values of this lane's 8 rows are requested before the accumulators are read, so
+                // their latency overlaps the TMEM load and the staging pass instead of sitting in the store loop
+                const int colp = col0 + ch * 4;
+                float4 oldc[8];
+                if (!TN && p.accumulate) {
+                    const float* gold = p.C + (size_t)z * p.bM * p.ldc + (size_t)row0 * p.ldc + colp;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + rsub;
+                        oldc[it] = (colp < p.N && row0 + rr < p.M) ? __ldg(reinterpret_cast<const float4*>(gold + (size_t)rr * p.ldc))
+                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
                 float* dst = stg + lane * 32;
@@ -175,7 +188,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     v.z = fmaxf(v.z, v.z * p.neg_slope); v.w = fmaxf(v.w, v.w * p.neg_slope);
                     if (col_ok && row0 + rr < p.M) {
                         float4* dstp = reinterpret_cast<float4*>(gcol + (size_t)rr * p.ldc);
-                        if (!TN && p.accumulate) { const float4 o = *dstp; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        if (!TN && p.accumulate) { const float4 o = oldc[it]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                         *dstp = v;
                     }
                 }
