@@ -230,16 +230,17 @@ edge_sel_stats_kernel(EdgeArgs a, const float* __restrict__ gamma, float* __rest
     const int c = g * 4;
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     if (active) {
-        float gm[4];
+        // the extremum is a MAXIMUM of sg * v with sg = +-1 (sign of gamma): one compare + two selects per element, no branch
+        float sg[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) gm[u] = gamma ? __ldg(gamma + c + u) : 1.f;
+        for (int u = 0; u < 4; ++u) sg[u] = (gamma ? __ldg(gamma + c + u) : 1.f) >= 0.f ? 1.f : -1.f;
         for (long long pt = (long long)blockIdx.x * lanes + lane; pt < a.M; pt += (long long)gridDim.x * lanes) {
             const long long cloud0 = (pt / a.N) * a.N;
             const int* ip = a.idx + pt * a.k;
             float best[4], sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
             int bi[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) best[u] = gm[u] >= 0.f ? -INFINITY : INFINITY;
+            for (int u = 0; u < 4; ++u) best[u] = -INFINITY;           // of sg * v
             // EDGE_U neighbour rows in flight per thread (the index -> row dependency chain was the whole cost of this loop);
             // the accumulation order stays m ascending
             for (int m0 = 0; m0 < a.k; m0 += EDGE_U) {
@@ -256,8 +257,10 @@ edge_sel_stats_kernel(EdgeArgs a, const float* __restrict__ gamma, float* __rest
                         const float v[4] = {vv[w].x, vv[w].y, vv[w].z, vv[w].w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const bool better = gm[u] >= 0.f ? (v[u] > best[u]) : (v[u] < best[u]);
-                            if (better) { best[u] = v[u]; bi[u] = m; }
+                            const float wv = v[u] * sg[u];                      // exact
+                            const bool better = wv > best[u];                   // strict: the first m reaching the extremum
+                            best[u] = better ? wv : best[u];
+                            bi[u] = better ? m : bi[u];
                             sum[u] += v[u];
                             sq[u] = fmaf(v[u], v[u], sq[u]);
                         }
@@ -269,7 +272,7 @@ edge_sel_stats_kernel(EdgeArgs a, const float* __restrict__ gamma, float* __rest
             float o[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                o[u] = best[u] + qv[u];
+                o[u] = best[u] * sg[u] + qv[u];
                 const double qd = qv[u];
                 s1[u] += (double)sum[u] + a.k * qd;
                 s2[u] += (double)sq[u] + 2.0 * qd * (double)sum[u] + a.k * qd * qd;
@@ -397,6 +400,8 @@ edge_bwd_kernel(EdgeArgs a, const float* __restrict__ bn, int act, float slope,
             sc[u] = __ldg(bn + c + u); sh[u] = __ldg(bn + C + c + u); mu[u] = __ldg(bn + 2 * C + c + u); is[u] = __ldg(bn + 3 * C + c + u);
             if (APPLY) { k1[u] = __ldg(S + c + u) * inv_count; k2[u] = __ldg(S + C + c + u) * inv_count; }
         }
+        // d act / d v of the edge layers' activations is a step function: 1 above zero, gneg below (NONE: 1, RELU: 0, LEAKY: slope)
+        const float gneg = act == LPD_ACT_LEAKY ? slope : (act == LPD_ACT_RELU ? 0.f : 1.f);
         for (long long pt = (long long)blockIdx.x * lanes + lane; pt < a.M; pt += (long long)gridDim.x * lanes) {
             const long long cloud0 = (pt / a.N) * a.N;
             const int* ip = a.idx + pt * a.k;
@@ -431,7 +436,7 @@ edge_bwd_kernel(EdgeArgs a, const float* __restrict__ bn, int act, float slope,
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const float zz = pv[u] + qv[u];
-                            const float d = (dyv[u] + (m == ar[u] ? dxv[u] : 0.f)) * act_grad(fmaf(sc[u], zz, sh[u]), act, slope, 0.f);
+                            const float d = (dyv[u] + (m == ar[u] ? dxv[u] : 0.f)) * (fmaf(sc[u], zz, sh[u]) > 0.f ? 1.f : gneg);
                             const float xh = (zz - mu[u]) * is[u];
                             if (APPLY) {
                                 o[u] = sc[u] * (d - k1[u] - xh * k2[u]);
@@ -625,6 +630,7 @@ extern "C" int lpd_edge_bwd_reduce(const float* p, int ldp, const float* q, int 
     int rc = edge_args(a, p, ldp, q, ldq, idx, B, N, k, C);
     if (rc != LPD_OK) return rc;
     LPD_REQUIRE(bn && partial && nparts >= 1 && (dx || dy) && (!dx || (arg && lddx % 4 == 0 && al16(dx))) && (!dy || al16(dy)));
+    LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || act == LPD_ACT_LEAKY);     // step-function gradients only
     edge_bwd_kernel<false><<<nparts, TR_THREADS, 0, as_stream(stream)>>>(a, bn, act, slope, dx, lddx, arg, dy, nullptr, 0.f, partial,
                                                                         nullptr, 0, nullptr, 0);
     LPD_LAUNCH_CHECK();
@@ -640,6 +646,7 @@ extern "C" int lpd_edge_bwd_apply(const float* p, int ldp, const float* q, int l
     if (rc != LPD_OK) return rc;
     LPD_REQUIRE(bn && S && dp && count >= 1 && (dx || dy) && (!dx || (arg && lddx % 4 == 0 && al16(dx))) && (!dy || al16(dy)));
     LPD_REQUIRE(lddp % 4 == 0 && al16(dp) && (!dq || (lddq % 4 == 0 && al16(dq))));
+    LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || act == LPD_ACT_LEAKY);     // step-function gradients only
     // dp accumulates with atomics: zero its C columns first
     LPD_CUDA_CHECK(cudaMemset2DAsync(dp, (size_t)lddp * 4, 0, (size_t)C * 4, (size_t)a.M, as_stream(stream)));
     edge_bwd_kernel<true><<<148 * 8, TR_THREADS, 0, as_stream(stream)>>>(a, bn, act, slope, dx, lddx, arg, dy, S, (float)(1.0 / count),
