@@ -24,6 +24,11 @@ __device__ __forceinline__ float act_grad(float v, int act, float slope, float a
     }
 }
 
+// NONE / RELU / LEAKY are piecewise linear: act(v) = v > 0 ? v : v * gneg and act'(v) = v > 0 ? 1 : gneg with gneg = 1 / 0 / slope.
+// The hot loops test this once per kernel (uniform branch) instead of switching per element.
+__device__ __forceinline__ bool act_is_step(int act) { return act == LPD_ACT_NONE || act == LPD_ACT_RELU || act == LPD_ACT_LEAKY; }
+__device__ __forceinline__ float act_gneg(int act, float slope) { return act == LPD_ACT_LEAKY ? slope : (act == LPD_ACT_RELU ? 0.f : 1.f); }
+
 // Block-level reduction of per-thread column accumulators.  Threads are laid out as (lane, g): g = column group of
 // 4 channels, `lanes` row lanes.  Writes partial[part][0][C] (s1) and partial[part][1][C] (s2).
 __device__ __forceinline__ void block_reduce_cols(double (&s1)[4], double (&s2)[4], int lane, int lanes, int g,
@@ -161,6 +166,8 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     const long long rpb = (rows + gridDim.x - 1) / gridDim.x;
     const long long r0 = (long long)blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
+    const bool step = act_is_step(act);
+    const float gneg = act_gneg(act, slope);
     if (active) {
         float sc[4], sh[4], mu[4], is[4];
 #pragma unroll
@@ -173,7 +180,8 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
             const float zv[4] = {zv4.x, zv4.y, zv4.z, zv4.w}, dv[4] = {dv4.x, dv4.y, dv4.z, dv4.w}, av[4] = {av4.x, av4.y, av4.z, av4.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float d = dv[u] * act_grad(fmaf(sc[u], zv[u], sh[u]), act, slope, av[u]);
+                const float pre = fmaf(sc[u], zv[u], sh[u]);
+                const float d = dv[u] * (step ? (pre > 0.f ? 1.f : gneg) : act_grad(pre, act, slope, av[u]));
                 const float xh = (zv[u] - mu[u]) * is[u];
                 s1[u] += d;
                 s2[u] += (double)d * xh;
@@ -188,11 +196,23 @@ __global__ void __launch_bounds__(TR_THREADS)
 bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ z, int ldz, long long rows, int C,
                     const float* __restrict__ bn, const float* __restrict__ S /* [2][C] */, float inv_count, int act, float slope,
                     const float* __restrict__ aux, int ldaux, float* __restrict__ dz, int lddz) {
-    const int cg = C >> 2;
-    const long long total = rows * cg;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long r = e / cg;
-        const int c = (int)(e % cg) * 4;
+    // thread = (row lane, group of 4 channels): the per-channel constants are loaded once, rows are walked with a grid stride
+    const int c0 = blockIdx.y * 1024;
+    const int Cb = min(1024, C - c0);
+    const int cg = Cb >> 2;
+    const int lanes = max(1, TR_THREADS / cg);
+    const int lane = threadIdx.x / cg, g = threadIdx.x % cg;
+    if (lane >= lanes) return;
+    const int c = c0 + g * 4;
+    const bool step = act_is_step(act);
+    const float gneg = act_gneg(act, slope);
+    float sc[4], sh[4], mu[4], is[4], k1[4], k2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        sc[u] = __ldg(bn + c + u); sh[u] = __ldg(bn + C + c + u); mu[u] = __ldg(bn + 2 * C + c + u); is[u] = __ldg(bn + 3 * C + c + u);
+        k1[u] = __ldg(S + c + u) * inv_count; k2[u] = __ldg(S + C + c + u) * inv_count;
+    }
+    for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
         const float4 zv4 = *reinterpret_cast<const float4*>(z + r * ldz + c);
         const float4 dv4 = *reinterpret_cast<const float4*>(dy + r * lddy + c);
         float4 av4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -201,10 +221,10 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restr
         float o[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float sc = __ldg(bn + c + u), sh = __ldg(bn + C + c + u), mu = __ldg(bn + 2 * C + c + u), is = __ldg(bn + 3 * C + c + u);
-            const float d = dv[u] * act_grad(fmaf(sc, zv[u], sh), act, slope, av[u]);
-            const float xh = (zv[u] - mu) * is;
-            o[u] = sc * (d - __ldg(S + c + u) * inv_count - xh * (__ldg(S + C + c + u) * inv_count));
+            const float pre = fmaf(sc[u], zv[u], sh[u]);
+            const float d = dv[u] * (step ? (pre > 0.f ? 1.f : gneg) : act_grad(pre, act, slope, av[u]));
+            const float xh = (zv[u] - mu[u]) * is[u];
+            o[u] = sc[u] * (d - k1[u] - xh * k2[u]);
         }
         *reinterpret_cast<float4*>(dz + r * lddz + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -290,6 +310,8 @@ edge_materialize_kernel(EdgeArgs a, const float* __restrict__ scale, const float
                         float* __restrict__ y) {
     const int cg = a.C >> 2;
     const long long total = a.M * a.k * cg;
+    const bool step = act_is_step(act);
+    const float gneg = act_gneg(act, slope);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long edge = e / cg;
         const int c = (int)(e % cg) * 4;
@@ -301,11 +323,13 @@ edge_materialize_kernel(EdgeArgs a, const float* __restrict__ scale, const float
         if (a.q) qv = __ldg(reinterpret_cast<const float4*>(a.q + pt * a.ldq + c));
         const float4 s = __ldg(reinterpret_cast<const float4*>(scale + c));
         const float4 t = __ldg(reinterpret_cast<const float4*>(shift + c));
-        float4 o;
-        o.x = apply_act(fmaf(s.x, pv.x + qv.x, t.x), act, slope);
-        o.y = apply_act(fmaf(s.y, pv.y + qv.y, t.y), act, slope);
-        o.z = apply_act(fmaf(s.z, pv.z + qv.z, t.z), act, slope);
-        o.w = apply_act(fmaf(s.w, pv.w + qv.w, t.w), act, slope);
+        float4 o = make_float4(fmaf(s.x, pv.x + qv.x, t.x), fmaf(s.y, pv.y + qv.y, t.y), fmaf(s.z, pv.z + qv.z, t.z), fmaf(s.w, pv.w + qv.w, t.w));
+        if (step) {
+            o.x = o.x > 0.f ? o.x : o.x * gneg; o.y = o.y > 0.f ? o.y : o.y * gneg;
+            o.z = o.z > 0.f ? o.z : o.z * gneg; o.w = o.w > 0.f ? o.w : o.w * gneg;
+        } else {
+            o.x = apply_act(o.x, act, slope); o.y = apply_act(o.y, act, slope); o.z = apply_act(o.z, act, slope); o.w = apply_act(o.w, act, slope);
+        }
         *reinterpret_cast<float4*>(y + edge * a.C + c) = o;
     }
 }
@@ -319,20 +343,31 @@ edge_sel_dense_kernel(const float* __restrict__ z, long long M, int k, int C, co
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long pt = e / cg;
         const int c = (int)(e % cg) * 4;
-        float gm[4], best[4];
+        float sg[4], best[4];                                 // maximum of sg * v, sg = sign of gamma (see edge_sel_stats_kernel)
         int bi[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { gm[u] = gamma ? __ldg(gamma + c + u) : 1.f; best[u] = gm[u] >= 0.f ? -INFINITY : INFINITY; }
-        for (int m = 0; m < k; ++m) {
-            const float4 v4 = __ldg(reinterpret_cast<const float4*>(z + (pt * k + m) * C + c));
-            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        for (int u = 0; u < 4; ++u) { sg[u] = (gamma ? __ldg(gamma + c + u) : 1.f) >= 0.f ? 1.f : -1.f; best[u] = -INFINITY; }
+        for (int m0 = 0; m0 < k; m0 += EDGE_U) {
+            float4 vv[EDGE_U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool better = gm[u] >= 0.f ? (v[u] > best[u]) : (v[u] < best[u]);
-                if (better) { best[u] = v[u]; bi[u] = m; }
+            for (int w = 0; w < EDGE_U; ++w)
+                vv[w] = (m0 + w < k) ? __ldg(reinterpret_cast<const float4*>(z + (pt * k + m0 + w) * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < EDGE_U; ++w) {
+                const int m = m0 + w;
+                if (m < k) {
+                    const float v[4] = {vv[w].x, vv[w].y, vv[w].z, vv[w].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float wv = v[u] * sg[u];
+                        const bool better = wv > best[u];
+                        best[u] = better ? wv : best[u];
+                        bi[u] = better ? m : bi[u];
+                    }
+                }
             }
         }
-        *reinterpret_cast<float4*>(zsel + pt * ldz + c) = make_float4(best[0], best[1], best[2], best[3]);
+        *reinterpret_cast<float4*>(zsel + pt * ldz + c) = make_float4(best[0] * sg[0], best[1] * sg[1], best[2] * sg[2], best[3] * sg[3]);
         *reinterpret_cast<uchar4*>(arg + pt * C + c) = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
     }
 }
@@ -569,7 +604,11 @@ extern "C" int lpd_bn_bwd_apply(const float* dy, int lddy, const float* z, int l
     LPD_REQUIRE(dy && z && bn && S && dz && rows >= 1 && C >= 4 && C % 4 == 0 && lddy % 4 == 0 && ldz % 4 == 0 && lddz % 4 == 0);
     LPD_REQUIRE(al16(dy) && al16(z) && al16(dz) && count >= 1);
     LPD_REQUIRE(act != LPD_ACT_GATE || (aux && ldaux % 4 == 0 && al16(aux)));
-    bn_bwd_apply_kernel<<<grid_for(rows * (C / 4)), TR_THREADS, 0, as_stream(stream)>>>(dy, lddy, z, ldz, rows, C, bn, S,
+    LPD_REQUIRE(C <= 1024 || C % 1024 == 0);
+    const int cgb = (C < 1024 ? C : 1024) / 4, lanes_b = TR_THREADS / cgb > 0 ? TR_THREADS / cgb : 1;
+    LPD_REQUIRE(cgb <= TR_THREADS);
+    dim3 grid_b(grid_for(rows, lanes_b), ceil_div(C, 1024));
+    bn_bwd_apply_kernel<<<grid_b, TR_THREADS, 0, as_stream(stream)>>>(dy, lddy, z, ldz, rows, C, bn, S,
                                                                                      (float)(1.0 / count), act, slope, aux, ldaux, dz, lddz);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
