@@ -96,8 +96,9 @@ def make_roofline(top, tot, cnt, step_ms, peaks, B):
                 "share_of_step": tot[top] / step_ms, "ms_per_launch": tot[top] / cnt[top], "note": "no algorithmic work model for this kernel"}
     flops, byts = work
     per_launch_ms = tot[top] / cnt[top]
-    # dense contractions (>= 16 FLOP per compulsory byte) are graded on the tensor pipe, streaming kernels on HBM
-    if flops > 0 and flops / byts >= 16.0:
+    # contractions with >= 64 FLOP per compulsory byte are graded on the tensor pipe; thin GEMMs (K or N <= 128: 30 FLOP/B,
+    # far below the ~210 FLOP/B ridge of the measured peaks) and streaming kernels on HBM bandwidth
+    if flops > 0 and flops / byts >= 64.0:
         tf = flops / (per_launch_ms * 1e-3) / 1e12
         return {"kernel": top, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": tf / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(top),
