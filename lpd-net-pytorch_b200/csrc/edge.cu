@@ -71,6 +71,32 @@ edge_gather_ext_kernel(const float* __restrict__ p, int ldp, const float* __rest
     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
     int m = 0;
+    if (tpp >= 32 && k <= 32) {
+        // a warp works on ONE point: its lanes fetch the k neighbour indices once and hand them round with shuffles, and the
+        // row address is one 32-bit multiply-add on a per-thread base (was: an index load + 64-bit address chain per row per thread)
+        const int lane = threadIdx.x & 31;
+        const int myj = lane < k ? __ldg(ip + lane) : 0;
+        const float* base = p + cloud0 * ldp + c;
+        for (; m + 5 <= k; m += 5) {
+            float4 v[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const int j = __shfl_sync(0xffffffffu, myj, m + u);
+                v[u] = __ldg(reinterpret_cast<const float4*>(base + (unsigned)(j * ldp)));
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                mx[0] = fmaxf(mx[0], v[u].x); mx[1] = fmaxf(mx[1], v[u].y); mx[2] = fmaxf(mx[2], v[u].z); mx[3] = fmaxf(mx[3], v[u].w);
+                mn[0] = fminf(mn[0], v[u].x); mn[1] = fminf(mn[1], v[u].y); mn[2] = fminf(mn[2], v[u].z); mn[3] = fminf(mn[3], v[u].w);
+            }
+        }
+        for (; m < k; ++m) {
+            const int j = __shfl_sync(0xffffffffu, myj, m);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (unsigned)(j * ldp)));
+            mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z); mx[3] = fmaxf(mx[3], v.w);
+            mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z); mn[3] = fminf(mn[3], v.w);
+        }
+    }
     for (; m + 4 <= k; m += 4) {
         float4 v[4];
 #pragma unroll
@@ -248,6 +274,7 @@ extern "C" int lpd_edge_gather_ext(const float* p, int ldp, const float* q, int 
     LPD_REQUIRE(ldp % 4 == 0 && ldo % 4 == 0 && ldp >= C && ldo >= C && (!q || (ldq % 4 == 0 && ldq >= C)));
     LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || act == LPD_ACT_LEAKY);
     LPD_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)q & 15) == 0);
+    LPD_REQUIRE((long long)N * ldp < (1ll << 31));          // cloud-local row offsets are 32-bit
     const long long total = (long long)B * N;
     const int ppb = 256 / (C / 4);
     const long long blocks = (total + ppb - 1) / ppb;

@@ -136,6 +136,7 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
                     myj = (lane < k) ? __ldg(P.idx + pt * k + lane) : 0;
                 }
                 float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                const float* pbase = P.p + cloud0 * P.ldp + lc * 4;   // row address = one 32-bit multiply-add on this base
                 constexpr int U = 10;                 // gathers in flight per lane
                 for (int m0 = 0; m0 < k; m0 += U * RPI) {
                     float4 pv[U];
@@ -143,7 +144,7 @@ edgeconv_dg_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, DgTcParams P)
                     for (int u = 0; u < U; ++u) {
                         const int m = m0 + u * RPI + sr;
                         const int j = __shfl_sync(kFull, myj, m & 31);
-                        if (m < k) pv[u] = __ldg(reinterpret_cast<const float4*>(P.p + (cloud0 + j) * P.ldp + lc * 4));
+                        if (m < k) pv[u] = __ldg(reinterpret_cast<const float4*>(pbase + (unsigned)(j * P.ldp)));
                     }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -290,6 +291,7 @@ extern "C" int lpd_edgeconv_dg_tf32(const float* p, int ldp, const float* q, int
     LPD_REQUIRE((C1 == 128 && C2 == 128) || (C1 == 64 && C2 == 64));
     LPD_REQUIRE(ldp % 4 == 0 && ldq % 4 == 0 && (!x1 || ld1 % 4 == 0));
     LPD_REQUIRE(ldp >= C1 && ldq >= C1 && ld2 >= C2 && (!x1 || ld1 >= C1));
+    LPD_REQUIRE((long long)N * ldp < (1ll << 31));          // cloud-local row offsets are 32-bit
     LPD_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)q & 15) == 0 && ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)w2 & 15) == 0);
     LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || (act == LPD_ACT_LEAKY && slope >= 0.f && slope <= 1.f));
     int dev = 0, major = 0;
