@@ -75,6 +75,8 @@ def kernel_work(label: str, B: int):
         return 0.0, 4.0 * B * N * (2 * C + C + k)
     if label == "lpd_netvlad_assign":
         return 2.0 * N * 1024 * 64 * B, 4.0 * B * N * (1024 + 64)
+    if label == "lpd_pointwise_mlp2":
+        return 2.0 * B * N * (3 * 64 + 64 * 64), 4.0 * B * N * (3 + 64)
     if label.startswith("lpd_knn_xyz"):
         return 2.0 * N * N * 3 * B, 4.0 * B * N * (3 + k)
     if label.startswith("lpd_edge_sel_stats") or label.startswith("lpd_edge_bwd_apply") or label.startswith("lpd_edge_bwd_reduce"):

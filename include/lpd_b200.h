@@ -168,6 +168,13 @@ int lpd_gemm_tf32_ex(const float* A, int lda, const float* B, int ldb, float* C,
 int lpd_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long strideC,
                      int M, int N, int K, int batch, void* stream);
 
+/* Fused input layers of the LPD-Net feature nets (lpdnet_model.py:231-232, :86-87), strict fp32, one pass:
+ *     out[m][:] = act(s2 * (W2 . act(s1 * (W1 . x[m][0..D)) + t1)) + t2),   W1 [64][D], W2 [64][64], D <= 8
+ * x [M][ldx], out [M][ldo]; act in {NONE, RELU, LEAKY with 0 <= slope <= 1}. */
+int lpd_pointwise_mlp2(const float* x, int ldx, int D, long long M, const float* w1, const float* s1, const float* t1,
+                       const float* w2, const float* s2, const float* t2, int act, float slope, float* out, int ldo,
+                       void* stream);
+
 /* column max over rows of each cloud: out[b][c] = max_n x[b][n][c]
  * (MaxPool2d((num_points,1)) PointNetVlad.py:137,169 ; torch.max(x,2) lpdnet_model.py:300) */
 int lpd_colmax(const float* x, int B, int N, int C, int ldx, float* out, void* stream);

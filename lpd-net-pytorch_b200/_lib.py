@@ -42,6 +42,7 @@ SIGNATURES = {
     "lpd_gemm_tf32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp]),
     "lpd_gemm_tf32_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp]),
     "lpd_gemm_tf32_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _ll, _i, _i, _i, _i, _vp]),
+    "lpd_pointwise_mlp2": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _vp]),
     "lpd_colmax": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "lpd_edge_gather_ext": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _i, _vp]),
     "lpd_edgeconv_dg": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f,

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import (ACT_ADD, ACT_GATE, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, A_KM, A_MK, B_KN, B_NK)
 
-__all__ = ["bn_fold", "transpose", "knn", "knn_tc_variant", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
+__all__ = ["bn_fold", "transpose", "knn", "knn_tc_variant", "pointwise_mlp2", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
            "gemm_tf32", "linear", "set_precision", "get_precision", "netvlad_assign", "softmax64", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
            "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ACT_SIGMOID", "ACT_GATE", "A_MK", "A_KM", "B_NK", "B_KN"]
 
@@ -234,6 +234,17 @@ def linear(A, W, *, M, N, K, lda=None, out=None, ldc=None, scale=None, shift=Non
             and (ldc is None or ldc % 4 == 0) and A.data_ptr() % 16 == 0 and (out is None or out.data_ptr() % 16 == 0)):
         return gemm_tf32(A, W, M=M, N=N, K=K, lda=lda, out=out, ldc=ldc, scale=scale, shift=shift, act=act, slope=slope)
     return gemm(A, W, M=M, N=N, K=K, lda=lda, out=out, ldc=ldc, scale=scale, shift=shift, act=act, slope=slope)
+
+
+def pointwise_mlp2(x, D, M, w1, s1, t1, w2, s2, t2, act=ACT_NONE, slope=0.0, ldx=None):
+    """out [M, 64] = act(s2 * (W2 . act(s1 * (W1 . x[:, :D]) + t1)) + t2): the two input 1x1 convs of the LPD-Net feature nets in
+    one strict-fp32 pass (the 64-wide hidden map stays in registers)."""
+    lib = _lib.load()
+    _f32(x, "x")
+    out = torch.empty(M, 64, device=x.device, dtype=torch.float32)
+    _call("lpd_pointwise_mlp2", 1, lib.lpd_pointwise_mlp2, x.data_ptr(), x.stride(-2) if ldx is None else ldx, D, M, w1.data_ptr(),
+          s1.data_ptr(), t1.data_ptr(), w2.data_ptr(), s2.data_ptr(), t2.data_ptr(), act, float(slope), out.data_ptr(), 64, _stream())
+    return out
 
 
 def colmax(x: torch.Tensor, B: int, N: int, C: int, ldx: int | None = None) -> torch.Tensor:

@@ -172,8 +172,11 @@ class _LPDBase(nn.Module):
             if self.t3d:
                 trans = self.t_net3d.forward_pm(rows, B, N, D)           # T-Net sees the raw xyz columns
                 rows = _apply_transform(rows, trans, B, N, 3, D)         # kNN below still uses xyz_init (reference :226,:255)
-            h = ops.linear(rows, p["w1"], M=M, N=64, K=D, scale=p["s1"], shift=p["t1"], act=act, slope=slope)
-            h = ops.linear(h, p["w2"], M=M, N=64, K=64, scale=p["s2"], shift=p["t2"], act=act, slope=slope)
+            if D <= 8 and p["w1"].shape[0] == 64 and tuple(p["w2"].shape) == (64, 64):
+                h = ops.pointwise_mlp2(rows, D, M, p["w1"], p["s1"], p["t1"], p["w2"], p["s2"], p["t2"], act, slope)
+            else:
+                h = ops.linear(rows, p["w1"], M=M, N=64, K=D, scale=p["s1"], shift=p["t1"], act=act, slope=slope)
+                h = ops.linear(h, p["w2"], M=M, N=64, K=64, scale=p["s2"], shift=p["t2"], act=act, slope=slope)
             if self.tfea:
                 tf = self.t_net_fea.forward_pm(h, B, N, 64)
                 h = _apply_transform(h, tf, B, N, 64, 64)

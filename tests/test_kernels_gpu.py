@@ -266,6 +266,27 @@ def test_retrieval_topk_vs_bruteforce_oracle(cuda, Ndb, Nq, D, k):
     assert np.array_equal(idx2.cpu().numpy()[want_idx >= 0], want_idx[want_idx >= 0] + 1000)
 
 
+@pytest.mark.parametrize("M,D,ld,act", [(1000, 3, 3, ops.ACT_LEAKY), (4096, 8, 8, ops.ACT_RELU), (130, 3, 5, ops.ACT_NONE), (70000, 3, 3, ops.ACT_LEAKY)])
+def test_pointwise_mlp2_matches_two_fp32_layers(cuda, M, D, ld, act):
+    """lpd_pointwise_mlp2 (conv1 + conv2 of the feature nets in one pass) == the two strict-fp32 layers, and == fp64 numpy"""
+    r = rng(M + D)
+    x = r.standard_normal((M, ld)).astype(np.float32)
+    w1 = (r.standard_normal((64, D)) / np.sqrt(D)).astype(np.float32)
+    w2 = (r.standard_normal((64, 64)) / 8).astype(np.float32)
+    s1, t1, s2, t2 = (r.standard_normal(64).astype(np.float32) for _ in range(4))
+    slope = 0.01
+
+    def a(v):
+        return v if act == ops.ACT_NONE else np.where(v > 0, v, (slope if act == ops.ACT_LEAKY else 0.0) * v)
+    ref = a((a((x[:, :D].astype(np.float64) @ w1.astype(np.float64).T) * s1 + t1) @ w2.astype(np.float64).T) * s2 + t2)
+    dx = dev(x)
+    got = ops.pointwise_mlp2(dx, D, M, dev(w1), dev(s1), dev(t1), dev(w2), dev(s2), dev(t2), act, slope).cpu().numpy()
+    assert np.abs(got - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    h = ops.gemm(dx, dev(w1), M=M, N=64, K=D, lda=ld, scale=dev(s1), shift=dev(t1), act=act, slope=slope)
+    two = ops.gemm(h, dev(w2), M=M, N=64, K=64, scale=dev(s2), shift=dev(t2), act=act, slope=slope).cpu().numpy()
+    assert np.abs(got - two).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core GEMM
 @pytest.mark.parametrize("M,N,K,ldx", [(1000, 1024, 512, 0), (128, 64, 1024, 0), (300, 512, 128, 0), (4096, 256, 64, 0),
                                        (777, 200, 96, 0), (2048, 128, 128, 512), (130, 1024, 40, 0)])
