@@ -40,18 +40,23 @@ pointwise_mlp2_kernel(const float* __restrict__ x, int ldx, int D, long long M, 
                 const float v = fmaf(s1s[c], acc, t1s[c]);
                 h1[c] = fmaxf(v, v * neg_slope);
             }
-#pragma unroll 2
-            for (int o = 0; o < 64; ++o) {
+            for (int o = 0; o < 64; o += 4) {                                        // four independent accumulation chains
                 const float4* wr = reinterpret_cast<const float4*>(w2s + o * 64);
-                float acc = 0.f;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int g = 0; g < 16; ++g) {
-                    const float4 w = wr[g];                                          // warp broadcast
-                    acc = fmaf(h1[4 * g + 0], w.x, acc); acc = fmaf(h1[4 * g + 1], w.y, acc);
-                    acc = fmaf(h1[4 * g + 2], w.z, acc); acc = fmaf(h1[4 * g + 3], w.w, acc);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w = wr[q * 16 + g];                             // warp broadcast
+                        acc[q] = fmaf(h1[4 * g + 0], w.x, acc[q]); acc[q] = fmaf(h1[4 * g + 1], w.y, acc[q]);
+                        acc[q] = fmaf(h1[4 * g + 2], w.z, acc[q]); acc[q] = fmaf(h1[4 * g + 3], w.w, acc[q]);
+                    }
                 }
-                const float v = fmaf(s2s[o], acc, t2s[o]);
-                stage[threadIdx.x * 65 + o] = fmaxf(v, v * neg_slope);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float v = fmaf(s2s[o + q], acc[q], t2s[o + q]);
+                    stage[threadIdx.x * 65 + o + q] = fmaxf(v, v * neg_slope);
+                }
             }
         }
         __syncthreads();
