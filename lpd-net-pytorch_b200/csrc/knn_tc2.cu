@@ -39,10 +39,13 @@
 //   3. rows whose list overflowed (masses of near-ties, e.g. duplicated points) or whose cloud could not be scaled flag
 //      their 64-row tile, which the exact CUDA-core kernel (knn.cu) recomputes.  Bit-identical to lpd_knn in every case.
 //
-// eps_i (in units of a = 2 x'_i.x'_j - nrm_j) = 2.5e-3 |x'_i| R' + 1.9e-6 (|x'_i| + R') / sigma + 2^-20 (xx_i + max xx) + 2^-18 R'^2:
-//   fp16 rounding of both operands (2^-11 relative each, 2^-25 absolute for subnormals; factor 2 of the score; 28 % spare),
-//   the fp32 accumulation of the tensor core including the K-extension (<= 2^-21 of the largest term), and the rounding of
-//   the canonical chain itself (<= 19 ulp of the norms).
+// eps_i (in units of a = 2 x'_i.x'_j - nrm_j) = 2.5e-3 |x'_i| R' + 1.9e-6 (|x'_i| + R') / sigma + 2^-17 (xx_i + max xx) + 2^-18 R'^2:
+//   * fp16 rounding of both operands (2^-11 relative each, 2^-25 absolute for subnormals; factor 2 of the score; 28 % spare);
+//   * the fp32 accumulation of the tensor core including the K-extension (<= 2^-21 of the largest term per step);
+//   * the WORST-CASE rounding of the canonical chain itself, which works on the UNcentred features: 64 fmaf steps give
+//     |dot_fp32 - dot| <= 64 u |x_i||x_j| (u = 2^-24), doubled by the -2, plus <= 66 u per squared norm and the two
+//     subtractions: <= 2^-17 (xx_i + max_j xx_j).  For features with a large common offset this term dominates and the
+//     filter degrades to the exact fallback - the canonical fp32 ranking itself is ill-conditioned there.
 //
 // What bounds it (ncu, B200, 64 clouds x 4096): the accumulators are read from TMEM at 64 B/clk/SM (4.3 GB in pass 1 alone
 // = 0.26 ms), and the MMA stream by itself (scan disabled) needs 0.31 ms: ~120 clk per 128 x 128 x 16 MMA, twice the
@@ -649,7 +652,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const float xxi = __ldg(P.xxpad + (size_t)b * P.Npad + row);
                 const float r2 = __ldg(P.r2 + b), r2c = __ldg(P.r2c + b), sigma = __ldg(P.sc + 2 * b);
                 const float rc = sqrtf(r2c);
-                float eps = (1.9e-6f / sigma) * (ni + rc) + 9.5367431640625e-7f * (xxi + r2) + 3.814697265625e-6f * r2c;
+                float eps = (1.9e-6f / sigma) * (ni + rc) + 7.62939453125e-6f * (xxi + r2) + 3.814697265625e-6f * r2c;
                 if (!TIGHT) eps += 2.5e-3f * ni * rc;
                 thr = fmaxf(tau0 - 2.f * eps * inv_cb, -1.0e9f);             // padded candidates sit near -2e9
                 if (!(eps * inv_cb < INFINITY)) thr = __int_as_float(0x7fc00000);   // unusable bound: collect nothing, fall back

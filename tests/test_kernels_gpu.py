@@ -419,7 +419,9 @@ def test_knn_tensor_core_filter_refine_is_bit_exact(cuda, B, N, k, kind, variant
     assert labels and labels[0].startswith("lpd_knn_tc")
     assert np.array_equal(got_simt, want)
     assert np.array_equal(got, want), f"{int((got != want).any(axis=2).sum())} rows differ; diag {diag}"
-    if variant != 0 and kind in ("relu", "big", "offset", "tiny", "huge"):
+    # ("offset": the worst-case rounding bound of the canonical chain on uncentred features dominates there, the filter may
+    # hand tiles to the exact kernel)
+    if variant != 0 and kind in ("relu", "big", "tiny", "huge"):
         assert diag["flagged_tiles"] == 0, diag
 
 

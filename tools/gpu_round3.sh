@@ -10,7 +10,7 @@ tail -15 $OUT/pytest_knn.log
 timeout 300 python tools/time_knn_variants.py 64 4096 20 > $OUT/time_knn_c2.log 2>&1; cat $OUT/time_knn_c2.log
 timeout 300 python tools/time_knn_variants.py 16 16384 32 > $OUT/time_knn_c5.log 2>&1; cat $OUT/time_knn_c5.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:knn2 -c 200 --csv --log-file $OUT/launches_knn.csv \
-    python tools/time_knn_variants.py 64 4096 20 12 > $OUT/ncu_knn.log 2>&1
+    python tools/time_knn_variants.py 64 4096 20 1 > $OUT/ncu_knn.log 2>&1
 python - <<PY
 import csv, collections
 rows = [r for r in csv.reader(open("$OUT/launches_knn.csv")) if len(r) > 5 and r[0].isdigit()]
