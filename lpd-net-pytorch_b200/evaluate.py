@@ -69,7 +69,9 @@ def get_recall(m, n, DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS):
 
 class _EmbedGraph:
     """One CUDA graph of `model(x)` for a fixed [batch, 1, N, 3] input (eval mode): the ~25 kernel launches of a step
-    replay without any host-side issue cost.  Invalidated when a parameter / buffer of the model changes."""
+    replay without any host-side issue cost.  Invalidated when a parameter / buffer of the model changes.  The graph keeps
+    the intermediates of one batch alive in its private memory pool (~3 GB for 64 x 4096 points) for as long as the model
+    holds it; `get_latent_vectors(..., use_graph=False)` or `del model._lpd_embed_graph` releases / avoids that."""
 
     def __init__(self, model, shape, dev):
         self.key = self._key(model)
