@@ -10,4 +10,4 @@ All arithmetic runs in liblpd_b200.so (include/lpd_b200.h); there is no CPU / to
 The directory is named `lpd-net-pytorch_b200` (not importable as-is); the sibling package
 `lpdnet_b200` aliases it.
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -17,6 +17,10 @@ def require_cuda(x: torch.Tensor, what: str) -> None:
                        f"(no CPU / torch fallback) — move the module and its input to cuda")
     if x.dtype != torch.float32:
         raise LpdError(f"{what}: expected float32 input, got {x.dtype}")
+    if x.device.index != torch.cuda.current_device():
+        raise LpdError(f"{what}: input is on {x.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; the "
+                       f"kernels launch on the current device's stream — use one process per GPU (torch.cuda.set_device) "
+                       f"instead of nn.DataParallel")
 
 
 def w2d(weight: torch.Tensor) -> torch.Tensor:
@@ -34,14 +38,16 @@ def fold_bn(bn: nn.modules.batchnorm._BatchNorm, bias: torch.Tensor | None = Non
 
 class Prepared:
     """Per-module cache of folded / re-laid-out weights, invalidated when any parameter or buffer changes
-    (in-place update bumps tensor._version; load_state_dict copies in place; .cuda() replaces tensors)."""
+    (in-place update bumps tensor._version; load_state_dict copies in place; .cuda() replaces tensors; the library's own
+    raw-pointer updates — lpd_adam, the running statistics of lpd_bn_finalize — bump ops.weights_epoch())."""
 
     def __init__(self):
         self._key = None
         self._val = None
 
     def get(self, module: nn.Module, builder):
-        key = tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+        key = (ops.weights_epoch(),) + tuple((t.data_ptr(), t._version)
+                                             for t in list(module.parameters()) + list(module.buffers()))
         if key != self._key:
             with torch.no_grad():
                 self._val = builder()

@@ -89,7 +89,9 @@ class _EmbedGraph:
 
     @staticmethod
     def _key(model):
-        return tuple((t.data_ptr(), t._version) for t in list(model.parameters()) + list(model.buffers()))
+        # parameters / buffers (torch-side and raw-pointer updates) + everything else the capture bakes in
+        return (ops.weights_epoch(), ops.dispatch_key()) + tuple((t.data_ptr(), t._version)
+                                                                 for t in list(model.parameters()) + list(model.buffers()))
 
     def valid_for(self, model, shape):
         return self.shape == tuple(shape) and self.key == self._key(model)

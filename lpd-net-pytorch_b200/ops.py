@@ -19,6 +19,26 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- weights epoch: kernels that update parameters / buffers through raw pointers (lpd_adam, lpd_bn_finalize's running
+# statistics) do not bump torch's tensor._version, so every cache keyed on the parameters (folded BatchNorm, re-laid-out
+# weights, captured CUDA graphs) also keys on this counter --------------------------------------------------------------
+_weights_epoch = 0
+
+
+def weights_epoch() -> int:
+    return _weights_epoch
+
+
+def bump_weights_epoch() -> None:
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def dispatch_key() -> tuple:
+    """everything outside the parameters that a captured forward bakes in (precision mode, kernel selection switches)"""
+    return (_precision, SPATIAL_ORDER, KNN_TENSOR_CORES, KNN_GRID, knn_tc_variant(-1) if _lib._lib is not None else -1)
+
+
 # ---- launch accounting / per-call device timing (used by bench.py; off by default) ----------------------------
 _launches = 0          # kernels launched through this module since reset_launch_count()
 _profile = None        # None, or a list receiving (label, start_event, end_event)
@@ -63,6 +83,11 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
         raise _lib.LpdError(f"{name} must be a CUDA tensor: the lpd_b200 kernels have no CPU path")
     if t.dtype != torch.float32:
         raise _lib.LpdError(f"{name} must be float32, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # the C ABI launches on the calling thread's current device / stream: one process (or at least one
+        # torch.cuda.device scope) per GPU; nn.DataParallel-style cross-device calls are rejected, not mis-launched
+        raise _lib.LpdError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                            f"call torch.cuda.set_device (one process per GPU) or wrap the call in torch.cuda.device(...)")
     return t
 
 
@@ -370,6 +395,8 @@ def bn_finalize(partial, nparts, count, C, gamma, beta, eps, momentum, running_m
     bn = torch.empty(4, C, device=partial.device, dtype=torch.float32)
     _call("lpd_bn_finalize", 1, lib.lpd_bn_finalize, partial.data_ptr(), nparts, float(count), C, _p(gamma), _p(beta), float(eps),
           float(momentum), _p(running_mean), _p(running_var), bn.data_ptr(), _stream())
+    if running_mean is not None or running_var is not None:
+        bump_weights_epoch()                                     # running statistics written through raw pointers
     return bn
 
 
@@ -551,6 +578,7 @@ def adam(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     lib = _lib.load()
     _call("lpd_adam", 1, lib.lpd_adam, w.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), w.numel(), float(lr), float(beta1),
           float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _stream())
+    bump_weights_epoch()                                         # parameters written through raw pointers
 
 
 def axpy(y, ldy, x, ldx, rows, C, alpha=1.0):

@@ -89,7 +89,6 @@ class Adam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        self._step += 1
         world = 1
         if self.allreduce and dist.is_available() and dist.is_initialized():
             world = dist.get_world_size(self.process_group)
@@ -97,18 +96,48 @@ class Adam(torch.optim.Optimizer):
             flat = self._flat.get(gi) or self._flatten(gi, group)
             if flat is None:
                 continue
-            for p, off, n, gv in flat["views"]:
+            steps = flat.setdefault("steps", [0] * len(flat["views"]))
+            active = []
+            for vi, (p, off, n, gv) in enumerate(flat["views"]):
                 if p.grad is None:
+                    # torch.optim.Adam skips such a parameter entirely (no moment decay, no weight decay, no step count);
+                    # its slice of the flat gradient stays zero for the all-reduce
                     gv.zero_()
-                elif p.grad.data_ptr() != gv.data_ptr():
+                    active.append(False)
+                    continue
+                if p.grad.data_ptr() != gv.data_ptr():
                     gv.copy_(p.grad)                                   # a caller replaced .grad: bring it into the flat buffer
                     p.grad = gv
-            if world > 1:
-                dist.all_reduce(flat["g"], op=dist.ReduceOp.SUM, group=self.process_group)
+                steps[vi] += 1
+                active.append(True)
+            self._reduce(flat, world)
             b1, b2 = group["betas"]
-            ops.adam(flat["w"], flat["g"], flat["m"], flat["v"], group["lr"], b1, b2, group["eps"], group["weight_decay"],
-                     self._step, 1.0 / world)
+            if all(active) and len(set(steps)) == 1:                   # the common case: ONE launch over the whole buffer
+                if steps:
+                    ops.adam(flat["w"], flat["g"], flat["m"], flat["v"], group["lr"], b1, b2, group["eps"],
+                             group["weight_decay"], steps[0], 1.0 / world)
+                continue
+            # some parameters received no gradient (or joined later): one launch per run of active segments with equal step
+            views = flat["views"]
+            vi = 0
+            while vi < len(views):
+                if not active[vi]:
+                    vi += 1
+                    continue
+                vj = vi
+                while vj + 1 < len(views) and active[vj + 1] and steps[vj + 1] == steps[vi]:
+                    vj += 1
+                lo, hi = views[vi][1], views[vj][1] + views[vj][2]
+                ops.adam(flat["w"][lo:hi], flat["g"][lo:hi], flat["m"][lo:hi], flat["v"][lo:hi], group["lr"], b1, b2,
+                         group["eps"], group["weight_decay"], steps[vi], 1.0 / world)
+                vi = vj + 1
+        self._step += 1
         return loss
+
+    def _reduce(self, flat, world):
+        """the data-parallel gradient sum: one NCCL all-reduce of the flat buffer on the current stream"""
+        if world > 1:
+            dist.all_reduce(flat["g"], op=dist.ReduceOp.SUM, group=self.process_group)
 
     # ---- torch.optim.Adam-compatible state ------------------------------------------------------------------------------
     def state_dict(self):
@@ -116,11 +145,12 @@ class Adam(torch.optim.Optimizer):
         state, idx = {}, 0
         for gi, group in enumerate(self.param_groups):
             flat = self._flat.get(gi)
-            lookup = {} if flat is None else {id(p): (off, n) for p, off, n, _ in flat["views"]}
+            lookup = {} if flat is None else {id(p): (off, n, vi) for vi, (p, off, n, _) in enumerate(flat["views"])}
+            steps = [] if flat is None else flat.get("steps", [0] * len(flat["views"]))
             for p in group["params"]:
-                if id(p) in lookup and self._step > 0:
-                    off, n = lookup[id(p)]
-                    state[idx] = {"step": torch.tensor(float(self._step)),
+                if id(p) in lookup and steps[lookup[id(p)][2]] > 0:
+                    off, n, vi = lookup[id(p)]
+                    state[idx] = {"step": torch.tensor(float(steps[vi])),
                                   "exp_avg": flat["m"][off:off + n].view(p.shape).clone(),
                                   "exp_avg_sq": flat["v"][off:off + n].view(p.shape).clone()}
                 idx += 1
@@ -129,6 +159,11 @@ class Adam(torch.optim.Optimizer):
 
     def load_state_dict(self, state_dict):
         groups = state_dict["param_groups"]
+        if len(groups) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        for group, saved in zip(self.param_groups, groups):
+            if "params" in saved and len(saved["params"]) != len(group["params"]):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
         for group, saved in zip(self.param_groups, groups):
             for key in ("lr", "betas", "eps", "weight_decay"):
                 if key in saved:
@@ -136,12 +171,14 @@ class Adam(torch.optim.Optimizer):
         idx = 0
         for gi, group in enumerate(self.param_groups):
             flat = self._flat.get(gi) or self._flatten(gi, group)
-            lookup = {} if flat is None else {id(p): (off, n) for p, off, n, _ in flat["views"]}
+            lookup = {} if flat is None else {id(p): (off, n, vi) for vi, (p, off, n, _) in enumerate(flat["views"])}
+            steps = None if flat is None else flat.setdefault("steps", [0] * len(flat["views"]))
             for p in group["params"]:
                 st = state_dict["state"].get(idx)
                 if st is not None and id(p) in lookup:
-                    off, n = lookup[id(p)]
+                    off, n, vi = lookup[id(p)]
                     flat["m"][off:off + n].copy_(st["exp_avg"].reshape(-1))
                     flat["v"][off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
-                    self._step = max(self._step, int(float(st["step"])))
+                    steps[vi] = int(float(st["step"]))
+                    self._step = max(self._step, steps[vi])
                 idx += 1

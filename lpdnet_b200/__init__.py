@@ -1,6 +1,6 @@
-"""Importable alias of the `lpd-net-pytorch_b200/` package directory (a hyphen cannot be imported)."""
+"""lpdnet_b200 — importable name of the `lpd-net-pytorch_b200/` package directory (a hyphen cannot be imported): the
+sub-modules are found there through __path__; see lpd-net-pytorch_b200/__init__.py for the public surface."""
 from pathlib import Path as _Path
 
-_real = _Path(__file__).resolve().parent.parent / "lpd-net-pytorch_b200"
-__path__ = [str(_real)]
-exec(compile((_real / "__init__.py").read_text(), str(_real / "__init__.py"), "exec"))
+__path__ = [str(_Path(__file__).resolve().parent.parent / "lpd-net-pytorch_b200")]
+__version__ = "0.2.0"

@@ -114,6 +114,58 @@ def test_train_then_eval_roundtrip_and_loss_decreases(cuda):
     assert torch.isfinite(out).all()
 
 
+def test_eval_after_lpd_adam_step_sees_the_updated_weights(cuda):
+    """eval -> lpdnet_b200 Adam step (raw-pointer update: tensor._version does not move) -> eval: the cached folded weights and
+    the captured embedding graph must be rebuilt.  featnet='pointnet' holds BatchNorm-free STNs whose cached fc3 bias + I is a
+    copy, i.e. the case nothing else invalidates."""
+    import copy
+    from lpdnet_b200 import evaluate
+    ops.set_precision("fp32")
+    model = PNV.PointNetVlad(num_points=256, featnet="pointnet", emb_dims=1024)
+    model.load_state_dict(synth.synthetic_state_dict(model))
+    model = model.cuda()
+    x = synth.clouds(22, 256)
+    clouds = synth.clouds(12, 256)[:, 0].numpy()
+    before = evaluate.get_latent_vectors(model, clouds, batch_num=4)          # caches Prepared + the CUDA graph
+    model.train()
+    opt = optim.Adam(model.parameters(), lr=1e-2)
+    for _ in range(2):
+        opt.zero_grad()
+        run_step(model, x, 1)
+        opt.step()
+    after = evaluate.get_latent_vectors(model, clouds, batch_num=4)
+    fresh = PNV.PointNetVlad(num_points=256, featnet="pointnet", emb_dims=1024).cuda()
+    fresh.load_state_dict(copy.deepcopy(model.state_dict()))                   # same weights, nothing cached
+    want = evaluate.get_latent_vectors(fresh, clouds, batch_num=4, use_graph=False)
+    assert np.abs(after - before).max() > 1e-4, "the optimizer steps did not change the descriptors"
+    assert np.array_equal(after, want), f"stale cache after lpd_adam: {np.abs(after - want).max():.3e}"
+
+
+def test_adam_skips_parameters_without_gradient(cuda):
+    """torch.optim.Adam leaves a parameter whose .grad is None untouched (no weight decay, no moment decay, no step count)"""
+    a = torch.nn.Parameter(torch.ones(1000, device="cuda"))
+    b = torch.nn.Parameter(torch.ones(777, device="cuda"))
+    c = torch.nn.Parameter(torch.ones(64, device="cuda"))
+    ra, rb, rc = (torch.nn.Parameter(t.detach().clone()) for t in (a, b, c))
+    opt = optim.Adam([a, b, c], lr=1e-2, weight_decay=0.1)
+    ref = torch.optim.Adam([ra, rb, rc], lr=1e-2, weight_decay=0.1)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for it in range(3):
+        for p, r in ((a, ra), (b, rb), (c, rc)):
+            g = torch.randn(p.shape, device="cuda", generator=gen)
+            skip = (p is b and it != 1)
+            p.grad = None if skip else g.clone()
+            r.grad = None if skip else g.clone()
+        opt.step()
+        ref.step()
+    for p, r in ((a, ra), (b, rb), (c, rc)):
+        assert torch.allclose(p, r, rtol=1e-5, atol=1e-6)
+    sd = opt.state_dict()["state"]
+    assert int(sd[0]["step"]) == 3 and int(sd[1]["step"]) == 1 and int(sd[2]["step"]) == 3
+    with pytest.raises(ValueError):
+        optim.Adam([a], lr=1e-2).load_state_dict(opt.state_dict())
+
+
 def test_training_step_tf32_mode_close_to_fp32(cuda, golden):
     """"tf32" precision mode (tensor-core GEMMs for the forward, input-gradient and weight-gradient products downstream
     of the kNN inputs): loss within 2e-3 relative of the reference, gradient L2 norms within 2 % of the fp64 reference."""
