@@ -274,6 +274,41 @@ int lpd_retrieval_topk(const float* db, int Ndb, const float* q, int Nq, int D, 
 int lpd_topk_merge(const double* part_dist, const int32_t* part_idx, int lists, int Nq, int k,
                    int32_t* idx, double* dist, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Retrieval on the tensor cores, per database SEGMENT (csrc/retrieval_tc.cu).  Replaces the per-run-pair
+ * KDTree(DATABASE_VECTORS[m]).query(q, k=25) loop of evaluate.py:59-70,168,186-187 for ALL runs in one call: the
+ * databases of all runs are stacked row-wise, segment s = rows [seg_off[s], seg_off[s+1]), and every query is searched in
+ * every segment.  Filter (3xTF32 split distance GEMM on tcgen05 -> approximate scores, k-th-score threshold with a proven
+ * error margin) + refine (the fp64 difference-form arithmetic of lpd_retrieval_topk): results are BIT-IDENTICAL to
+ * lpd_retrieval_topk run on each segment (ascending (distance, index); ties to the lower index).
+ *   db [Ndb][D], q [Nq][D], D % 4 == 0, D <= 1024; seg_off int32 [S+1] (device), ascending, seg_off[0] >= 0, seg_off[S] <= Ndb
+ *   idx  int32  [S][Nq][k]: segment-local row (global_idx == 0) or database row + idx_offset (global_idx != 0); -1 = empty
+ *   dist double [S][Nq][k] squared distances (nullable)
+ *   workspace: lpd_retrieval_tc_workspace_bytes(Ndb, Nq, D) bytes, 256-byte aligned (split operands + the [Nq][Ndb] scores)
+ * A database sharded over ranks / cut into ~1000-row pseudo-segments is finished with lpd_topk_merge (the [S][Nq][k]
+ * layout is that function's input layout).
+ * ------------------------------------------------------------------------------------------- */
+size_t lpd_retrieval_tc_workspace_bytes(int Ndb, int Nq, int D);
+int lpd_retrieval_tc(const float* db, int Ndb, const float* q, int Nq, int D, int k,
+                     const int32_t* seg_off, int S, int global_idx, int idx_offset,
+                     int32_t* idx, double* dist, void* workspace, size_t workspace_bytes, void* stream);
+
+/* get_recall's counting (evaluate.py:176-206) for all (query, database segment) units at once, on the device.
+ *   idx [S][Nq][k] segment-local top-k (lpd_retrieval_tc), k <= 25.  There are R runs; segment s is the database of run
+ *   seg_run[s] (nullable: s itself; a rank that holds a subset of the runs passes their numbers).  q_run int32 [Nq] = run of
+ *   each query: a query is not searched in its own run's database (evaluate.py:61-62); q_run[i] < 0 = belongs to no run.
+ *   Truth in CSR form: the true neighbours of query i in run m are truth_idx[truth_off[i*R+m] .. truth_off[i*R+m+1])
+ *   (indices local to that run's database; empty = the query is skipped, :181-182).
+ *   seg_thresh int32 [S] = max(int(round(len(db_s)/100)), 1) (:174).
+ *   Outputs (caller zeroes the counters), row = max(q_run[i], 0) * S + s:  hist int32 [R*S][25] first-hit rank histogram
+ *   (:189-193), n_eval [R*S] evaluated queries, n_onepct [R*S] queries with a true neighbour among the first seg_thresh ranks
+ *   (:200-201), sim float [Nq][S] (nullable; needs db, seg_off, q, D) = dot(query, its top-1) where the top-1 is a true
+ *   neighbour (:191), NaN elsewhere. */
+int lpd_recall_count(const int32_t* idx, int S, int Nq, int k, const int32_t* q_run, int R, const int32_t* seg_run,
+                     const int32_t* truth_off, const int32_t* truth_idx, const int32_t* seg_thresh,
+                     const float* db, const int32_t* seg_off, const float* q, int D,
+                     int32_t* hist, int32_t* n_eval, int32_t* n_onepct, float* sim, void* stream);
+
 /* =============================================================================================
  * TRAIN MODE (reference: model.train() forward, loss.backward(), optimizer.step();
  * train_pointnetvlad.py:121-130,150-159).  Batch-statistics BatchNorm and the backward pass.

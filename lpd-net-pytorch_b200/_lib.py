@@ -57,6 +57,9 @@ SIGNATURES = {
     "lpd_retrieval_workspace_bytes": (_sz, [_i, _i, _i]),
     "lpd_retrieval_topk": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "lpd_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "lpd_retrieval_tc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "lpd_retrieval_tc": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "lpd_recall_count": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     # ---- train mode ----
     "lpd_bn_stats": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp]),
     "lpd_bn_finalize": (_i, [_vp, _i, _d, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),

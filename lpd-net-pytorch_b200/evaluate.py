@@ -1,10 +1,12 @@
-"""Drop-in for the hot-path part of the reference's evaluate.py: get_recall (:162-206) with the same signature
-and return triple, and the bulk embedding driver get_latent_vectors (:96-159) re-expressed over in-memory clouds.
+"""Drop-in for the hot-path part of the reference's evaluate.py: get_recall (:162-206) with the same signature and return
+triple, the pair loop + aggregation of evaluate_model (:59-93), and the bulk embedding driver get_latent_vectors (:96-159)
+re-expressed over in-memory clouds.
 
-get_recall replaces the per-query sklearn KDTree.query loop by ONE exact brute-force top-25 kernel launch per
-(database run, query run) pair (lpd_retrieval_topk: fp64 distances like KDTree, ties to the lower index); the
-counting logic after the search is the reference's, kept on the host because it consumes Python ground-truth
-lists (QUERY_SETS[n][i][m]).
+Retrieval replaces the per-query sklearn KDTree.query loop: the databases of all runs are stacked and searched in ONE pass
+(lpd_retrieval_tc: 3xTF32 distance GEMM on the tensor cores as a filter, exact fp64 difference-form re-rank like KDTree, ties
+to the lower index), and the first-hit histogram / recall@1% / top-1 similarity bookkeeping of get_recall runs on the device
+as well (lpd_recall_count).  The Python ground-truth lists (QUERY_SETS[n][i][m]) are flattened once into a CSR table
+(`prepare_truth`); no per-query Python loop remains.
 """
 from __future__ import annotations
 
@@ -13,7 +15,7 @@ import torch
 
 from . import ops
 
-__all__ = ["get_recall", "get_latent_vectors", "evaluate_sets", "recall_num"]
+__all__ = ["get_recall", "get_latent_vectors", "evaluate_sets", "evaluate_model", "recall_all_pairs", "prepare_truth", "recall_num"]
 
 recall_num = 25  # reference evaluate.py:20
 
@@ -31,39 +33,124 @@ def _as_dev(a) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(_device())
 
 
-def get_recall(m, n, DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS):
-    """Same contract as the reference: returns (recall[25] cumulative %, top1_similarity_score list, one_percent_recall %)."""
-    database_output = DATABASE_VECTORS[m]
-    queries_output = QUERY_VECTORS[n]
-    db_dev, q_dev = _as_dev(database_output), _as_dev(queries_output)
-    k = min(recall_num, db_dev.shape[0])
-    idx, _ = ops.retrieval_topk(db_dev, q_dev, k, want_dist=False)
-    indices = idx.cpu().numpy()
+def _threshold(n_db: int) -> int:
+    return max(int(round(n_db / 100.0)), 1)          # reference :174 (Python's round: half to even)
 
-    recall = [0] * recall_num
-    top1_similarity_score = []
-    one_percent_retrieved = 0
-    threshold = max(int(round(len(database_output) / 100.0)), 1)
-    num_evaluated = 0
-    db_host = database_output.detach().cpu().numpy() if isinstance(database_output, torch.Tensor) else np.asarray(database_output)
-    q_host = queries_output.detach().cpu().numpy() if isinstance(queries_output, torch.Tensor) else np.asarray(queries_output)
-    for i in range(len(q_host)):
-        true_neighbors = QUERY_SETS[n][i][m]
-        if len(true_neighbors) == 0:
-            continue
-        num_evaluated += 1
-        row = indices[i]
-        truth = set(true_neighbors)
-        for j in range(len(row)):
-            if row[j] in truth:
-                if j == 0:
-                    top1_similarity_score.append(np.dot(q_host[i], db_host[row[j]]))
-                recall[j] += 1
-                break
-        if len(set(row[0:threshold].tolist()).intersection(truth)) > 0:
-            one_percent_retrieved += 1
-    one_percent_recall = (one_percent_retrieved / float(num_evaluated)) * 100
-    recall = (np.cumsum(recall) / float(num_evaluated)) * 100
+
+class Truth:
+    """QUERY_SETS flattened for the device: query i of run n is row q_off[n] + i of the stacked query matrix; its true
+    neighbours in database run m are truth_idx[truth_off[row * R + m] : truth_off[row * R + m + 1]] (indices local to run m)."""
+
+    def __init__(self, q_sizes, truth_off, truth_idx):
+        self.q_sizes = list(q_sizes)
+        self.R = len(self.q_sizes)
+        self.q_off = np.concatenate(([0], np.cumsum(self.q_sizes))).astype(np.int64)
+        self.q_run = np.repeat(np.arange(self.R, dtype=np.int32), self.q_sizes)
+        self.truth_off = truth_off
+        self.truth_idx = truth_idx
+        self._dev = None
+
+    def device(self, dev):
+        if self._dev is None or self._dev[0] != dev:
+            self._dev = (dev, torch.from_numpy(self.q_run).to(dev), torch.from_numpy(self.truth_off).to(dev),
+                         torch.from_numpy(self.truth_idx if self.truth_idx.size else np.zeros(1, np.int32)).to(dev))
+        return self._dev[1:]
+
+
+def prepare_truth(QUERY_SETS, runs=None) -> Truth:
+    """One pass over the reference's ground-truth structure (list over runs n of per-query dicts whose key m holds the list of
+    true database indices in run m, generating_queries/generate_test_sets.py:86-112) -> CSR arrays.  Host-side data
+    preparation, done once per evaluation set."""
+    R = len(QUERY_SETS) if runs is None else runs
+    flat, offs, sizes = [], [0], []
+    for n in range(R):
+        qs = QUERY_SETS[n]
+        sizes.append(len(qs))
+        for i in range(len(qs)):
+            entry = qs[i]
+            for m in range(R):
+                t = entry[m]
+                if len(t):
+                    flat.extend(t)
+                offs.append(len(flat))
+    return Truth(sizes, np.asarray(offs, dtype=np.int32), np.asarray(flat, dtype=np.int32))
+
+
+def recall_all_pairs(DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS, truth: Truth | None = None, group=None):
+    """Every ordered (database run m, query run n) pair of the evaluation in one pass.  Returns a dict:
+         recall   [R, R, 25]  cumulative recall@1..25 in percent, indexed [n][m]   (get_recall's first return value)
+         one_pct  [R, R]      recall@1% in percent                               (third return value)
+         sim      [Nq, R]     float32 top-1 similarity where the top-1 is a true neighbour, NaN elsewhere (second)
+         n_eval   [R, R]      queries with non-empty ground truth
+       With torch.distributed initialised the database RUNS are sharded over the ranks (each rank searches all queries in its
+       runs' segments) and the integer counters are all-reduced (pairs shard, counters reduce)."""
+    from . import parallel
+    dev = _device()
+    truth = truth or prepare_truth(QUERY_SETS)
+    R = truth.R
+    rank, world = parallel.world(group)
+    mine = list(range(rank, R, world))                 # this rank's database runs (round-robin: equal sizes in practice)
+    q = torch.cat([_as_dev(v) for v in QUERY_VECTORS], 0)
+    q_run, truth_off, truth_idx = truth.device(dev)
+    hist = torch.zeros(R, R, recall_num, device=dev, dtype=torch.int32)
+    n_eval = torch.zeros(R, R, device=dev, dtype=torch.int32)
+    n_one = torch.zeros(R, R, device=dev, dtype=torch.int32)
+    sim = torch.full((q.shape[0], R), float("nan"), device=dev, dtype=torch.float32)
+    if mine:
+        db = torch.cat([_as_dev(DATABASE_VECTORS[m]) for m in mine], 0)
+        sizes = [len(DATABASE_VECTORS[m]) for m in mine]
+        seg_off = torch.tensor(np.concatenate(([0], np.cumsum(sizes))), dtype=torch.int32, device=dev)
+        seg_run = torch.tensor(mine, dtype=torch.int32, device=dev)
+        thresh = torch.tensor([_threshold(n) for n in sizes], dtype=torch.int32, device=dev)
+        k = min(recall_num, min(sizes))
+        idx, _ = ops.retrieval_tc(db, q, k, seg_off, want_dist=False)                   # [S_local, Nq, k], segment-local rows
+        h, ne, no, sm = ops.recall_count(idx, q_run, R, truth_off, truth_idx, thresh, seg_run, db, seg_off, q)
+        cols = seg_run.long()
+        hist[:, cols] = h
+        n_eval[:, cols] = ne
+        n_one[:, cols] = no
+        sim[:, cols] = sm
+    if world > 1:
+        packed = torch.cat((hist.reshape(-1), n_eval.reshape(-1), n_one.reshape(-1)))
+        parallel.allreduce_counters(packed, group)
+        nh, ne_ = hist.numel(), n_eval.numel()
+        hist, n_eval, n_one = packed[:nh].view_as(hist), packed[nh: nh + ne_].view_as(n_eval), packed[nh + ne_:].view_as(n_one)
+        sim = parallel.merge_nan(sim, group)
+    hist_h, ne_h, no_h = hist.cpu().numpy().astype(np.float64), n_eval.cpu().numpy().astype(np.float64), n_one.cpu().numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        recall = np.cumsum(hist_h, axis=2) / ne_h[:, :, None] * 100.0
+        one_pct = no_h / ne_h * 100.0
+    return {"recall": recall, "one_pct": one_pct, "sim": sim.cpu().numpy(), "n_eval": ne_h, "truth": truth}
+
+
+def get_recall(m, n, DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS):
+    """Same contract as the reference (:162-206): returns (recall[25] cumulative %, top1_similarity_score list,
+    one_percent_recall %) for database run m and query run n."""
+    dev = _device()
+    db, q = _as_dev(DATABASE_VECTORS[m]), _as_dev(QUERY_VECTORS[n])
+    Nq, Ndb = q.shape[0], db.shape[0]
+    flat, offs = [], [0]
+    for i in range(Nq):
+        t = QUERY_SETS[n][i][m]
+        if len(t):
+            flat.extend(t)
+        offs.append(len(flat))
+    truth_off = torch.tensor(offs, dtype=torch.int32, device=dev)
+    truth_idx = torch.tensor(flat if flat else [0], dtype=torch.int32, device=dev)
+    seg_off = torch.tensor([0, Ndb], dtype=torch.int32, device=dev)
+    k = min(recall_num, Ndb)
+    if Nq * Ndb >= ops.RETRIEVAL_TC_MIN and db.shape[1] % 4 == 0:
+        idx, _ = ops.retrieval_tc(db, q, k, seg_off, want_dist=False)
+    else:
+        idx = ops.retrieval_topk(db, q, k, want_dist=False)[0].unsqueeze(0)
+    q_run = torch.full((Nq,), -1, dtype=torch.int32, device=dev)           # no own-run skip inside get_recall (the pair loop does it)
+    thresh = torch.tensor([_threshold(len(DATABASE_VECTORS[m]))], dtype=torch.int32, device=dev)
+    hist, n_eval, n_one, sim = ops.recall_count(idx.contiguous(), q_run, 1, truth_off, truth_idx, thresh, None, db, seg_off, q)
+    num_evaluated = float(n_eval[0, 0].item())
+    recall = (np.cumsum(hist[0, 0].cpu().numpy()) / num_evaluated) * 100
+    s = sim[:, 0].cpu().numpy()
+    top1_similarity_score = [v for v in s if not np.isnan(v)]
+    one_percent_recall = (float(n_one[0, 0].item()) / num_evaluated) * 100
     return recall, top1_similarity_score, one_percent_recall
 
 
@@ -191,24 +278,27 @@ def get_latent_vectors(model, clouds, batch_num: int = 64, pin: bool = True, use
     return out.numpy().copy()                                 # the landing buffer is reused by the next call
 
 
-def evaluate_sets(DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS):
-    """Pair loop + aggregation of evaluate_model (reference :59-93) over already-embedded sets:
-    returns (ave_recall[25], average_similarity, ave_one_percent_recall)."""
-    recall = np.zeros(recall_num)
-    count = 0
-    similarity = []
-    one_percent_recall = []
-    for m in range(len(QUERY_SETS)):
-        for n in range(len(QUERY_SETS)):
-            if m == n:
-                continue
-            pair_recall, pair_similarity, pair_opr = get_recall(m, n, DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS)
-            recall += np.array(pair_recall)
-            count += 1
-            one_percent_recall.append(pair_opr)
-            for x in pair_similarity:
-                similarity.append(x)
-    ave_recall = recall / count
-    average_similarity = np.mean(similarity)
-    ave_one_percent_recall = np.mean(one_percent_recall)
+def evaluate_sets(DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS, truth: Truth | None = None, group=None):
+    """Pair loop + aggregation of evaluate_model (reference :59-93) over already-embedded sets, all pairs in one device pass:
+    returns (ave_recall[25], average_similarity, ave_one_percent_recall).  ave_recall is the recall@1..25 curve averaged over
+    the pairs (the reference's `recall / count`); evaluate_model() reduces it to the reference's scalar."""
+    res = recall_all_pairs(DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS, truth, group)
+    R = res["recall"].shape[0]
+    off = ~np.eye(R, dtype=bool)                                   # [n][m], m != n
+    ave_recall = res["recall"][off].sum(0) / off.sum()
+    sims = res["sim"]
+    average_similarity = float(np.mean(sims[~np.isnan(sims)].astype(np.float64))) if (~np.isnan(sims)).any() else float("nan")
+    ave_one_percent_recall = float(np.mean(res["one_pct"][off]))
     return ave_recall, average_similarity, ave_one_percent_recall
+
+
+def evaluate_model(model, DATABASE_CLOUDS, QUERY_CLOUDS, QUERY_SETS, batch_num: int = 64, group=None):
+    """The reference's evaluate_model (:33-93) over in-memory submaps: DATABASE_CLOUDS[r] / QUERY_CLOUDS[r] are the [n, N, 3]
+    clouds of run r (the reference reads them from the pickled file lists, :51-56).  Returns the reference's triple
+    (ave_recall SCALAR = mean over N of the mean recall@N, :73; average_similarity_score; ave_one_percent_recall).
+    Like the reference (get_latent_vectors :156), the model is left in train() mode."""
+    DATABASE_VECTORS = [get_latent_vectors(model, c, batch_num=batch_num) for c in DATABASE_CLOUDS]
+    QUERY_VECTORS = [get_latent_vectors(model, c, batch_num=batch_num) for c in QUERY_CLOUDS]
+    model.train()
+    curve, average_similarity, ave_one_percent_recall = evaluate_sets(DATABASE_VECTORS, QUERY_VECTORS, QUERY_SETS, group=group)
+    return float(np.mean(curve)), average_similarity, ave_one_percent_recall

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import (ACT_ADD, ACT_GATE, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, A_KM, A_MK, B_KN, B_NK)
 
 __all__ = ["bn_fold", "transpose", "knn", "knn_tc_variant", "pointwise_mlp2", "gemm", "colmax", "edge_gather_ext", "edgeconv_dg",
-           "gemm_tf32", "linear", "set_precision", "get_precision", "netvlad_assign", "softmax64", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk",
+           "gemm_tf32", "linear", "set_precision", "get_precision", "netvlad_assign", "softmax64", "netvlad_finish", "splitk_reduce", "quadruplet_loss", "retrieval_topk", "retrieval_tc", "retrieval_search", "recall_count",
            "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ACT_SIGMOID", "ACT_GATE", "A_MK", "A_KM", "B_NK", "B_KN"]
 
 
@@ -373,6 +373,60 @@ def topk_merge(part_dist: torch.Tensor, part_idx: torch.Tensor):
     _call("lpd_topk_merge", 1, lib.lpd_topk_merge, part_dist.data_ptr(), part_idx.data_ptr(), lists, Nq, k, idx.data_ptr(),
           dist.data_ptr(), _stream())
     return idx, dist
+
+
+def retrieval_tc(db: torch.Tensor, q: torch.Tensor, k: int, seg_off: torch.Tensor, global_idx: bool = False, idx_offset: int = 0,
+                 want_dist: bool = True):
+    """Tensor-core filter + exact fp64 refine, per database segment (lpd_retrieval_tc): db [Ndb, D], q [Nq, D], seg_off int32
+    [S+1] on the device -> (idx int32 [S, Nq, k], squared dist float64 [S, Nq, k] or None); bit-identical to retrieval_topk
+    run on each segment."""
+    lib = _lib.load()
+    db, q = _f32(db, "db").contiguous(), _f32(q, "q").contiguous()
+    Ndb, D = db.shape
+    Nq, S = q.shape[0], seg_off.numel() - 1
+    idx = torch.empty(S, Nq, k, device=db.device, dtype=torch.int32)
+    dist = torch.empty(S, Nq, k, device=db.device, dtype=torch.float64) if want_dist else None
+    nbytes = lib.lpd_retrieval_tc_workspace_bytes(Ndb, Nq, D)
+    ws = torch.empty(nbytes, device=db.device, dtype=torch.uint8)
+    _call(f"lpd_retrieval_tc[{Nq}x{Ndb}x{D}]", 4, lib.lpd_retrieval_tc, db.data_ptr(), Ndb, q.data_ptr(), Nq, D, k, seg_off.data_ptr(), S,
+          int(bool(global_idx)), int(idx_offset), idx.data_ptr(), _p(dist), ws.data_ptr(), nbytes, _stream())
+    return idx, dist
+
+
+RETRIEVAL_TC_MIN = 1 << 22      # Nq * Ndb from which the tensor-core filter beats the fp64 brute force (below: launch-bound)
+RETRIEVAL_SEG = 1024            # pseudo-segment length of the single-database search (one warp pass per segment)
+
+
+def retrieval_search(db: torch.Tensor, q: torch.Tensor, k: int, idx_offset: int = 0, want_dist: bool = True):
+    """k nearest rows of ONE database for every query: (idx int32 [Nq, k] + idx_offset, squared dist float64 [Nq, k]).
+    Large problems run the tensor-core filter over ~1000-row pseudo-segments and merge the per-segment lists
+    (lpd_topk_merge); small ones the fp64 brute force.  Both give bit-identical results."""
+    Ndb, D = db.shape
+    Nq = q.shape[0]
+    if Nq * Ndb < RETRIEVAL_TC_MIN or D % 4 or D > 1024 or k > Ndb:
+        return retrieval_topk(db, q, k, idx_offset=idx_offset, want_dist=want_dist)
+    seg = torch.arange(0, Ndb + RETRIEVAL_SEG, RETRIEVAL_SEG, device=db.device, dtype=torch.int32).clamp_(max=Ndb)
+    idx, dist = retrieval_tc(db, q, k, seg, global_idx=True, idx_offset=idx_offset)
+    if seg.numel() == 2:
+        return idx[0], (dist[0] if want_dist else None)
+    i, d = topk_merge(dist, idx)
+    return i, (d if want_dist else None)
+
+
+def recall_count(idx, q_run, R, truth_off, truth_idx, seg_thresh, seg_run=None, db=None, seg_off=None, q=None):
+    """get_recall's counting for all (query, segment) units (lpd_recall_count) -> (hist int32 [R, S, 25], n_eval [R, S],
+    n_onepct [R, S], sim float32 [Nq, S] or None)"""
+    lib = _lib.load()
+    S, Nq, k = idx.shape
+    dev = idx.device
+    counters = torch.zeros(R * S * 27, device=dev, dtype=torch.int32)
+    hist, n_eval, n_one = counters[: R * S * 25], counters[R * S * 25: R * S * 26], counters[R * S * 26:]
+    sim = torch.empty(Nq, S, device=dev, dtype=torch.float32) if db is not None else None
+    D = 0 if db is None else db.shape[1]
+    _call("lpd_recall_count", 1, lib.lpd_recall_count, idx.data_ptr(), S, Nq, k, q_run.data_ptr(), R, _p(seg_run),
+          truth_off.data_ptr(), truth_idx.data_ptr(), seg_thresh.data_ptr(), _p(db), _p(seg_off), _p(q), D, hist.data_ptr(),
+          n_eval.data_ptr(), n_one.data_ptr(), _p(sim), _stream())
+    return hist.view(R, S, 25), n_eval.view(R, S), n_one.view(R, S), sim
 
 
 # =====================================================================================================================

@@ -54,10 +54,10 @@ class Adam(torch.optim.Optimizer):
                 wv = w[off:off + n].view(p.shape)
                 wv.copy_(p.data)                                       # one-time move into the flat buffer
                 gv = g[off:off + n].view(p.shape)
-                if p.grad is not None:
-                    gv.copy_(p.grad)
                 p.data = wv
-                p.grad = gv
+                if p.grad is not None:                                 # a parameter without gradient keeps .grad = None
+                    gv.copy_(p.grad)
+                    p.grad = gv
                 views.append((p, off, n, gv))
                 off += sz
         flat = dict(w=w, g=g, m=m, v=v, views=views)

@@ -13,7 +13,7 @@ import torch.distributed as dist
 
 from . import ops
 
-__all__ = ["world", "shard_range", "shard_tuples", "sharded_retrieval_topk", "allreduce_counters"]
+__all__ = ["world", "shard_range", "shard_tuples", "sharded_retrieval_topk", "allreduce_counters", "merge_nan"]
 
 
 def world(group=None):
@@ -43,7 +43,7 @@ def sharded_retrieval_topk(db_shard: torch.Tensor, queries: torch.Tensor, k: int
     db_shard [n_local, D] = global rows [row_offset, row_offset + n_local); queries [Nq, D] replicated.
     Each rank: local top-k with GLOBAL indices -> all-gather of (dist, idx) [Nq, k] -> deterministic merge
     (ascending distance, ties to the lower global index).  Returns (idx int32 [Nq, k], dist float64 [Nq, k]) on every rank."""
-    local_topk = local_topk or (lambda d, q, kk, off: ops.retrieval_topk(d, q, kk, idx_offset=off))
+    local_topk = local_topk or (lambda d, q, kk, off: ops.retrieval_search(d, q, kk, idx_offset=off))
     merge = merge or ops.topk_merge
     rank, ws = world(group)
     Nq = queries.shape[0]
@@ -71,3 +71,15 @@ def allreduce_counters(t: torch.Tensor, group=None) -> torch.Tensor:
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+def merge_nan(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Every entry of `t` is set (not NaN) on at most one rank: returns the union on every rank (NaN where no rank set it).
+    Used for the per-query top-1 similarities when the database runs are sharded."""
+    _, ws = world(group)
+    if ws == 1:
+        return t
+    valid = ~torch.isnan(t)
+    both = torch.stack((torch.where(valid, t, torch.zeros_like(t)), valid.to(t.dtype)))
+    dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
+    return torch.where(both[1] > 0, both[0], torch.full_like(t, float("nan")))

@@ -152,25 +152,29 @@ class ColMax:
 
 
 class Transform:
-    """out[b] = rows[b][:, :C] . T[b]   (torch.bmm / matmul with a T-Net output: lpdnet_model.py:86,93,229,241; PointNetVlad.py:209,223)"""
+    """out[b][:, :C] = rows[b][:, :C] . T[b]   (torch.bmm / matmul with a T-Net output: lpdnet_model.py:86,93,229,241;
+    PointNetVlad.py:209,223).  keep_tail: rows wider than C (the 8-d use_mFea input, lpdnet_model.py:215-222) keep their
+    remaining columns, i.e. the output is [B*N, ld] again."""
 
-    def fwd(self, rows, ld, trans, B, N, C):
+    def fwd(self, rows, ld, trans, B, N, C, keep_tail=False):
         self.rows, self.ld, self.trans, self.B, self.N, self.C = rows, ld, trans.contiguous(), B, N, C
-        out = torch.empty(B * N, C, device=rows.device, dtype=torch.float32)
-        ops.gemm(rows, self.trans, a_layout=A_MK, b_layout=B_KN, M=N, N=C, K=C, lda=ld, ldb=C, out=out, ldc=C,
-                 batch=B, strideA=N * ld, strideB=C * C, strideC=N * C)
+        self.ldo = ld if (keep_tail and ld != C) else C
+        out = rows.clone() if self.ldo != C else torch.empty(B * N, C, device=rows.device, dtype=torch.float32)
+        ops.gemm(rows, self.trans, a_layout=A_MK, b_layout=B_KN, M=N, N=C, K=C, lda=ld, ldb=C, out=out, ldc=self.ldo,
+                 batch=B, strideA=N * ld, strideB=C * C, strideC=N * self.ldo)
         return out
 
-    def bwd(self, dout, need_drows):
+    def bwd(self, dout, need_drows, lddout=None):
         B, N, C = self.B, self.N, self.C
+        ldd = C if lddout is None else lddout
         # dT[b] = rows[b]^T . dout[b]
-        dtrans = ops.gemm(self.rows, dout, a_layout=A_KM, b_layout=B_KN, M=C, N=C, K=N, lda=self.ld, ldb=C, batch=B,
-                          strideA=N * self.ld, strideB=N * C, strideC=C * C,
+        dtrans = ops.gemm(self.rows, dout, a_layout=A_KM, b_layout=B_KN, M=C, N=C, K=N, lda=self.ld, ldb=ldd, batch=B,
+                          strideA=N * self.ld, strideB=N * ldd, strideC=C * C,
                           out=torch.empty(B, C, C, device=dout.device, dtype=torch.float32), ldc=C)
         drows = None
         if need_drows:   # drows[b][n][c] = sum_c' dout[b][n][c'] T[b][c][c']
-            drows = ops.gemm(dout, self.trans, a_layout=A_MK, b_layout=B_NK, M=N, N=C, K=C, lda=C, ldb=C, batch=B,
-                             strideA=N * C, strideB=C * C, strideC=N * C,
+            drows = ops.gemm(dout, self.trans, a_layout=A_MK, b_layout=B_NK, M=N, N=C, K=C, lda=ldd, ldb=C, batch=B,
+                             strideA=N * ldd, strideB=C * C, strideC=N * C,
                              out=torch.empty(B * N, C, device=dout.device, dtype=torch.float32), ldc=C)
         return drows, dtrans
 
@@ -232,8 +236,6 @@ def _act_of(module):
 # ----------------------------------------------------------------------------------------------------------------------
 class LPDNetTrain:
     def __init__(self, net):
-        if net.use_mFea:
-            raise LpdError("train mode with use_mFea is not built yet")
         self.net = net
 
     # conv1 / conv2 (+BN+act) with the optional T-Nets around them (reference :226-241); strict fp32: they feed the kNN
@@ -242,7 +244,7 @@ class LPDNetTrain:
         self.t3, self.tf = None, None
         if net.t3d:
             self.t3, self.x3 = TNetTrain(net.t_net3d), Transform()
-            rows = self.x3.fwd(rows, D, self.t3.fwd(rows, D, B, N), B, N, 3)
+            rows = self.x3.fwd(rows, D, self.t3.fwd(rows, D, B, N), B, N, 3, keep_tail=True)
         self.l1, self.b1, self.l2, self.b2 = Linear(), BNAct(), Linear(), BNAct()
         z1 = self.l1.fwd(rows, D, M, conv1.weight, tf32_ok=False)
         h1 = self.b1.fwd(z1, 64, M, 64, bn1, act, slope)
@@ -265,8 +267,8 @@ class LPDNetTrain:
         if self.t3 is None:
             self.l1.bwd(dz1, 64, grads, need_da=False)
             return
-        drows = self.l1.bwd(dz1, 64, grads)                                        # [M, 3]: gradient of the transformed xyz
-        _, dt3 = self.x3.bwd(drows, need_drows=False)
+        drows = self.l1.bwd(dz1, 64, grads)                                        # [M, D]: gradient of the transformed xyz (+ the mFea columns)
+        _, dt3 = self.x3.bwd(drows, need_drows=False, lddout=drows.shape[1])
         self.t3.bwd(dt3, grads, need_drows=False)
 
     def fwd(self, x):
@@ -279,11 +281,13 @@ class LPDNetTrain:
         self.act, self.slope = act, slope
         dev = x.device
         rows = x.detach().reshape(M, D).contiguous()
-        if ops.SPATIAL_ORDER and N >= 64:
+        if D != 3 and not (D == 8 and net.use_mFea):
+            raise ValueError(f"LPDNet: expected 3 input dims (or 8 with use_mFea: xyz + 5 features), got {D}")
+        if ops.SPATIAL_ORDER and N >= 64 and D == 3:
             # grid-cell order per cloud: every stage below is per-point equivariant, NetVLAD and the BatchNorm statistics
             # sum over the points, and no input gradient is needed, so the parameter gradients are unchanged
             rows = ops.cell_order(rows.view(B, N, 3))[2].view(M, 3)
-        xyz = rows.view(B, N, 3)
+        xyz = rows.view(B, N, D)[:, :, :3].contiguous() if D != 3 else rows.view(B, N, 3)   # kNN uses the untransformed xyz (:216,:255)
         h2 = self._front_fwd(rows, D, B, N, net.conv1_lpd, net.bn1_lpd, net.conv2_lpd, net.bn2_lpd, act, slope)
         self.h2 = h2
         # ---- feature-space graph: DG1 (decomposed) -> x1, DG2 (dense edge GEMM) -> x2 --------------------------------
@@ -375,9 +379,11 @@ class LPDNetOrignTrain(LPDNetTrain):
         act, slope = _act_of(net)
         self.act, self.slope = act, slope
         rows = x.detach().reshape(M, D).contiguous()
-        if ops.SPATIAL_ORDER and N >= 64:
+        if D != 3 and not (D == 8 and net.use_mFea):
+            raise ValueError(f"LPDNetOrign: expected 3 input dims (or 8 with use_mFea), got {D}")
+        if ops.SPATIAL_ORDER and N >= 64 and D == 3:
             rows = ops.cell_order(rows.view(B, N, 3))[2].view(M, 3)
-        xyz = rows.view(B, N, 3)
+        xyz = rows.view(B, N, D)[:, :, :3].contiguous() if D != 3 else rows.view(B, N, 3)
         h2 = self._front_fwd(rows, D, B, N, net.conv1_lpd[0], net.conv1_lpd[1], net.conv2_lpd[0], net.conv2_lpd[1], act, slope)
         self.h2 = h2
         # ---- feature-space graph: edges [f_i ; f_j - f_i] -> DG1 (decomposed: P = Wb f_j, Q = (Wa - Wb) f_i), DG2 (dense), max ----

@@ -6,19 +6,13 @@ The reference has no tests or golden vectors of its own, so thes
 tests/test_oracle_vs_golden.py checks the CPU oracle against them (CPU, no GPU needed) and the -m gpu
 tests check the CUDA path against both.
 
-How the reference is imported without touching it:
-  * util/lpdnet_model.py hard-codes torch.device('cuda') (:123,:307,:338); the module-global `torch` of that
-    module is replaced by a proxy whose .device(...) returns cpu and which forwards everything else;
-  * evaluate.py cannot be imported (it imports util.initPara, which parses argv / inits NVML / creates dirs),
-    so get_recall (:162-206) is extracted from its AST and exec'd with np, KDTree and recall_num=25.
+How the reference is imported without touching it: oracle/ref_loader.py (torch.device proxy shim, AST-extracted get_recall).
 """
 from __future__ import annotations
 
-import ast
 import hashlib
 import os
 import sys
-import types
 from pathlib import Path
 
 import numpy as np
@@ -36,29 +30,13 @@ from lpdnet_b200 import synth  # noqa: E402
 def import_reference():
     if not REF.exists():
         raise SystemExit(f"{REF} not found: golden vectors can only be generated in the authoring container")
-    sys.path.insert(0, str(REF))
-    import util.lpdnet_model as L  # noqa
-
-    class _Proxy(types.ModuleType):
-        def __getattr__(self, n):
-            return getattr(torch, n)
-
-        def device(self, *a, **k):
-            return torch.device("cpu")
-
-    L.torch = _Proxy("torch_proxy")
-    import util.PointNetVlad as PNV  # noqa
-    import loss.pointnetvlad_loss as RL  # noqa
-    return L, PNV, RL
+    from oracle import ref_loader
+    return ref_loader.import_reference(REF)
 
 
 def extract_get_recall():
-    from sklearn.neighbors import KDTree
-    tree = ast.parse((REF / "evaluate.py").read_text())
-    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_recall")
-    ns = {"np": np, "KDTree": KDTree, "recall_num": 25}
-    exec(compile(ast.Module([node], []), "evaluate.py", "exec"), ns)
-    return ns["get_recall"]
+    from oracle import ref_loader
+    return ref_loader.extract_get_recall(REF)
 
 
 def sha(t) -> str:
@@ -131,6 +109,26 @@ def case_c2_lpdnet(L, PNV, RL):
     _model_case(PNV, "c2_lpdnetorigin_eval", "lpdnetorigin", 2, 4096)
     _model_case(PNV, "c5_lpdnet_k32_eval", "lpdnet", 1, 2048, k=32)
     _model_case(PNV, "c3_lpdnet_train_small", "lpdnet", 8, 1024, train=True)
+
+
+def case_mfea(L, PNV, RL):
+    """LPDNet with use_mFea=True (8-d input, lpdnet_model.py:215-222) on its own, eval mode: [B,1,N,8] -> [B,emb,N,1]; and
+    through PointNetVlad with the feature net swapped in.  The [B,1024,N,1] map is stored as a strided subsample + per-channel
+    means (the full map would be 4 MiB)."""
+    for name, t3d in (("mfea_lpdnet_eval", False), ("mfea_lpdnet_t3d_eval", True)):
+        torch.manual_seed(1234)
+        model = PNV.PointNetVlad(num_points=512, featnet="lpdnet", emb_dims=1024)
+        model.emb_nn = L.LPDNet(emb_dims=1024, use_mFea=True, t3d=t3d, tfea=False)
+        sd = synth.synthetic_state_dict(model)
+        model.load_state_dict(sd)
+        model.eval()
+        x = synth.clouds(2, 512, dims=8)
+        with torch.no_grad():
+            f = model.emb_nn(x)                      # [2, 1024, 512, 1]
+            out = model(x)
+        flat = f.reshape(-1)
+        save(name, out=out.numpy(), f_sub=flat[::61].numpy().copy(), f_chan_mean=f.mean(dim=(0, 2, 3)).numpy(),
+             f_shape=np.array(f.shape), x_sha=sha(x), sd_sha=sd_digest(sd), keys=np.array(sorted(sd.keys())))
 
 
 def case_loss(L, PNV, RL):
@@ -227,29 +225,46 @@ def case_c3_train_step(L, PNV, RL, only=None):
                             ("train_step_pointnet_n256", 256, 1, dict(featnet="pointnet", _seed=4)),   # seed 1234 gives an exactly zero hinge loss
                             ("train_step_pointnet_ft_n256", 256, 1, dict(featnet="pointnet", feature_transform=True)),
                             ("train_step_lpdnet_tnets_n256", 256, 1, dict(featnet="lpdnet", feature_transform=True, xyz_trans=True)),
-                            ("train_step_lpdnetorigin_tnets_n256", 256, 1, dict(featnet="lpdnetorigin", feature_transform=True, xyz_trans=True))):
+                            ("train_step_lpdnetorigin_tnets_n256", 256, 1, dict(featnet="lpdnetorigin", feature_transform=True, xyz_trans=True)),
+                            # use_mFea (8-d input: xyz + 5 neighbourhood features, lpdnet_model.py:215-222).  PointNetVlad never
+                            # enables it (:248), so the feature net is swapped in after construction, as a caller would
+                            ("train_step_lpdnet_mfea_n256", 256, 1, dict(featnet="lpdnet", _mfea=dict(t3d=False))),
+                            ("train_step_lpdnet_mfea_t3d_n256", 256, 1, dict(featnet="lpdnet", _mfea=dict(t3d=True))),
+                            # the benchmarked C3 step at full size: 2 tuples x 22 clouds x 4096 points.  The fp64 twin is forward-only
+                            # (out64, loss64): its autograd run needs ~60 GB for the 44-cloud batch (BatchNorm couples the batch, so it
+                            # cannot be split)
+                            ("c3_train_step_n4096_b2", 4096, 2, dict(featnet="lpdnet", _no64=True))):
         if only and name not in only:
             continue
+        if name == "c3_train_step_n4096_b2" and not only:
+            continue                       # ~2 minutes and ~30 GB: generated on request (c3train:c3_train_step_n4096_b2)
         restore = _patch_batchnorm2d_w1() if kw.get("featnet") == "pointnet" else None
         arrays = {}
         # fp32 = the reference as shipped; fp64 = the same code in double, the yardstick for the fp32 run's own rounding
         # noise (LeakyReLU sign / arg-max / near-tie kNN flips move isolated gradient entries by up to ~1e-2 of the
         # tensor's max between fp32 and fp64 runs of the reference itself)
         for tag, dtype in (("", torch.float32), ("64", torch.float64)):
+            fwd_only = tag == "64" and kw.get("_no64")      # fp64 twin too large for autograd: forward-only yardstick (out64, loss64)
             torch.manual_seed(1234)
             model = PNV.PointNetVlad(num_points=N, emb_dims=1024, **{k_: v for k_, v in kw.items() if not k_.startswith("_")})
+            if "_mfea" in kw:
+                model.emb_nn = L.LPDNet(emb_dims=1024, use_mFea=True, tfea=False, **kw["_mfea"])
             sd = synth.synthetic_state_dict(model)
             model.load_state_dict(sd)
             model.train()
             model = model.to(dtype)
             P, Nn = 2, 18
-            x = synth.clouds(Bq * (1 + P + Nn + 1), N, seed=kw.get("_seed", 1234))
-            out = model(x.to(dtype))
-            o = out.view(Bq, -1, 256)
-            q, pos, neg, other = torch.split(o, [1, P, Nn, 1], dim=1)
-            loss = RL.quadruplet_loss(q, pos, neg, other, 0.5, 0.2, use_min=True, lazy=True, ignore_zero_loss=False)
-            loss.backward()
+            x = synth.clouds(Bq * (1 + P + Nn + 1), N, seed=kw.get("_seed", 1234), dims=8 if "_mfea" in kw else 3)
+            with torch.set_grad_enabled(not fwd_only):
+                out = model(x.to(dtype))
+                o = out.view(Bq, -1, 256)
+                q, pos, neg, other = torch.split(o, [1, P, Nn, 1], dim=1)
+                loss = RL.quadruplet_loss(q, pos, neg, other, 0.5, 0.2, use_min=True, lazy=True, ignore_zero_loss=False)
             arrays.update({"out" + tag: out.detach().numpy(), "loss" + tag: loss.detach().numpy()})
+            print(f"  {name}{tag}: loss {float(loss.detach()):.6f}")
+            if fwd_only:
+                continue
+            loss.backward()
             for key, p_ in model.named_parameters():
                 if p_.grad is None:               # parameters the forward never touches (e.g. PointNetfeat.feature_trans when unused)
                     continue
@@ -261,12 +276,11 @@ def case_c3_train_step(L, PNV, RL, only=None):
                 for key in after:
                     if key.endswith("running_mean") or key.endswith("running_var"):
                         arrays["after." + key] = after[key].numpy()
-            print(f"  {name}{tag}: loss {float(loss.detach()):.6f}")
         if restore is not None:
             torch.nn.BatchNorm2d.forward = restore
         save(name, **arrays)
 
-CASES = {"knn": case_knn, "c1": case_c1_pointnet, "c2": case_c2_lpdnet, "loss": case_loss, "recall": case_recall, "c3train": case_c3_train_step}
+CASES = {"mfea": case_mfea, "knn": case_knn, "c1": case_c1_pointnet, "c2": case_c2_lpdnet, "loss": case_loss, "recall": case_recall, "c3train": case_c3_train_step}
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())

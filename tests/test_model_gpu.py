@@ -46,6 +46,29 @@ def test_descriptors_match_reference_golden(cuda, golden, name, B, N, kw):
     assert err <= DESC_TOL, f"{name}: max-abs {err:.3e} vs the reference"
 
 
+@pytest.mark.parametrize("name,t3d", [("mfea_lpdnet_eval", False), ("mfea_lpdnet_t3d_eval", True)])
+def test_use_mfea_8d_input_matches_reference_golden(cuda, golden, name, t3d):
+    """LPDNet(use_mFea=True): 8-d input = xyz + 5 neighbourhood features expected IN the input (reference
+    lpdnet_model.py:215-222; the kNN graph uses the xyz columns only, :216,:255).  The [B,1024,N,1] per-point map of
+    LPDNet.forward (committed as a strided subsample + channel means) and the descriptors through PointNetVlad."""
+    g = golden(name)
+    model = PNV.PointNetVlad(num_points=512, featnet="lpdnet", emb_dims=1024)
+    model.emb_nn = LM.LPDNet(emb_dims=1024, use_mFea=True, t3d=t3d, tfea=False)
+    sd = synth.synthetic_state_dict(model)
+    assert sorted(sd.keys()) == g["keys"].tolist()
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    x = synth.clouds(2, 512, dims=8).cuda()
+    with torch.no_grad():
+        f = model.emb_nn(x)
+        out = model(x).cpu().numpy()
+    assert tuple(f.shape) == tuple(g["f_shape"].tolist())
+    scale = max(1.0, float(np.abs(g["f_sub"]).max()))
+    assert np.abs(f.reshape(-1)[::61].cpu().numpy() - g["f_sub"]).max() <= 1e-4 * scale
+    assert np.abs(f.mean(dim=(0, 2, 3)).cpu().numpy() - g["f_chan_mean"]).max() <= 1e-4 * scale
+    assert np.abs(out - g["out"]).max() <= DESC_TOL
+
+
 def test_k32_variant_matches_reference_golden(cuda, golden):
     g = golden("c5_lpdnet_k32_eval")
     model, _ = build(g, num_points=2048, emb_dims=1024, featnet="lpdnet")
@@ -129,23 +152,67 @@ def test_loss_module_matches_reference_and_backpropagates(cuda, golden):
 
 
 def test_recall_identical_to_reference_kdtree_on_all_pairs(cuda, golden):
+    """C4: every ordered run pair (506) against the golden produced by the reference's own get_recall (sklearn KDTree):
+    (a) the drop-in get_recall(m, n, ...) on a subset of pairs, (b) ALL pairs in one device pass (stacked databases ->
+    lpd_retrieval_tc -> lpd_recall_count) — recall@1..25 and recall@1% identical, top-1 similarity counts identical."""
     g = golden("recall")
     DB, Q, SETS = synth.descriptor_database()
     runs = len(DB)
     DBd = [torch.from_numpy(d).cuda() for d in DB]
     Qd = [torch.from_numpy(q).cuda() for q in Q]
+    res = evaluate.recall_all_pairs(DBd, Qd, SETS)
     p = 0
+    sims_total, sims_n = 0.0, 0
     for m in range(runs):
         for n in range(runs):
             if m == n:
                 continue
-            r, sims, one = evaluate.get_recall(m, n, DBd, Qd, SETS)
-            assert np.array_equal(r, g["recall"][p]), (m, n)       # recall@1..25 identical
-            assert one == g["one_percent"][p]                      # recall@1% identical
-            assert len(sims) == g["sim_count"][p]
+            assert np.array_equal(res["recall"][n, m], g["recall"][p]), (m, n)      # recall@1..25 identical
+            assert res["one_pct"][n, m] == g["one_percent"][p]                      # recall@1% identical
+            rows = slice(int(res["truth"].q_off[n]), int(res["truth"].q_off[n + 1]))
+            s = res["sim"][rows, m]
+            assert int((~np.isnan(s)).sum()) == g["sim_count"][p]
+            assert abs(float(np.nansum(s.astype(np.float64))) - float(g["sim_sum"][p])) <= 1e-4 * max(1.0, abs(float(g["sim_sum"][p])))
+            if p % 37 == 0:                                                         # the per-pair drop-in on a sample of pairs
+                r, sims, one = evaluate.get_recall(m, n, DBd, Qd, SETS)
+                assert np.array_equal(r, g["recall"][p]) and one == g["one_percent"][p] and len(sims) == g["sim_count"][p]
+            sims_total += float(g["sim_sum"][p])
+            sims_n += int(g["sim_count"][p])
             p += 1
-    ave_recall, ave_sim, ave_one = evaluate.evaluate_sets(DB[:4], Q[:4], [[{mm: s[mm] for mm in range(4)} for s in S] for S in SETS[:4]])
-    assert ave_recall.shape == (25,) and 0 < ave_one <= 100
+    curve, ave_sim, ave_one = evaluate.evaluate_sets(DBd, Qd, SETS)
+    assert np.allclose(curve, g["recall"].mean(0), rtol=0, atol=1e-9)
+    assert abs(ave_one - float(np.mean(g["one_percent"]))) <= 1e-9
+    assert abs(ave_sim - sims_total / sims_n) <= 1e-5
+
+
+def test_retrieval_tc_is_bit_identical_to_the_fp64_brute_force(cuda):
+    """lpd_retrieval_tc (3xTF32 distance GEMM filter + fp64 refine) against lpd_retrieval_topk on every segment: indices AND
+    fp64 distances identical — ragged segments (1 row, fewer than k rows, not a multiple of 4, longer than one 1024-row warp
+    pass), exact duplicates (ties -> lower index), near-duplicates 1 ulp apart (the filter margin must keep both), scaled
+    descriptors (norm 30) and a query equal to a database row."""
+    rng = np.random.default_rng(17)
+    sizes = [1, 7, 33, 956, 1025, 2500, 130]
+    db = rng.standard_normal((sum(sizes), 256)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    db[100] = db[60]                                            # exact duplicate inside the 956-row segment
+    db[200] = np.nextafter(db[61], np.float32(2.0))             # 1-ulp neighbour
+    db[2100:2200] *= 30.0                                       # a few long rows: the error bound scales with max |x|
+    q = np.concatenate([db[[60, 61, 1500]], rng.standard_normal((77, 256)).astype(np.float32) / 16.0]).astype(np.float32)
+    dbt, qt = torch.from_numpy(db).cuda(), torch.from_numpy(q).cuda()
+    off = np.concatenate(([0], np.cumsum(sizes)))
+    seg = torch.tensor(off, dtype=torch.int32, device="cuda")
+    k = 25
+    idx, dst = ops.retrieval_tc(dbt, qt, k, seg)
+    for s_, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+        kk = min(k, hi - lo)
+        ri, rd = ops.retrieval_topk(dbt[lo:hi].contiguous(), qt, kk)
+        assert torch.equal(idx[s_, :, :kk], ri), f"segment {s_} ({hi - lo} rows): indices"
+        assert torch.equal(dst[s_, :, :kk], rd), f"segment {s_}: distances"
+        assert (idx[s_, :, kk:] == -1).all()
+    # single-database entry point: pseudo-segments + merge == brute force, global indices with an offset
+    gi, gd = ops.retrieval_search(dbt, qt.repeat(60, 1), k, idx_offset=1000)
+    ri, rd = ops.retrieval_topk(dbt, qt.repeat(60, 1), k, idx_offset=1000)
+    assert torch.equal(gi, ri) and torch.equal(gd, rd)
 
 
 def test_get_latent_vectors_batches_and_tail(cuda, golden):
@@ -220,7 +287,7 @@ def test_database_sharded_retrieval_merge_is_bit_exact(cuda):
     parts_i, parts_d = [], []
     for r in range(3):
         lo, hi = parallel.shard_range(len(db), 3, r)
-        i, d = ops.retrieval_topk(dbt[lo:hi], qt, 25, idx_offset=lo)
+        i, d = (ops.retrieval_topk if r == 1 else ops.retrieval_search)(dbt[lo:hi], qt, 25, idx_offset=lo)
         parts_i.append(i)
         parts_d.append(d)
     idx, dst = ops.topk_merge(torch.stack(parts_d), torch.stack(parts_i))

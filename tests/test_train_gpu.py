@@ -76,6 +76,56 @@ def test_training_step_matches_reference_autograd(cuda, golden, name, N, Bq):
             assert np.allclose(got, g[key], rtol=1e-4, atol=1e-5), f"{key[6:]} after one train step"
 
 
+def test_full_size_c3_step_matches_reference_autograd(cuda, golden):
+    """The benchmarked C3 configuration itself: 2 tuples x 22 clouds x 4096 points, train-mode forward, lazy quadruplet loss,
+    backward — against the UNMODIFIED reference (oracle/gen_golden.py c3train:c3_train_step_n4096_b2): its fp32 CPU autograd
+    run, plus a forward-only fp64 run as the yardstick (the fp64 autograd run needs ~60 GB).
+
+    At this size the reference's OWN fp32 forward is 5.5e-3 max-abs away from its fp64 forward in the descriptors and 2.5e-4
+    relative in the loss (44-sample batch-statistics BatchNorm after sums over 4096 points and 81,920 edges per cloud; the
+    N = 512 twin of this step shows 2.5e-5).  So the bars are, with noise = |reference fp32 - reference fp64|:
+      descriptors   <= max(1e-4, 1.05 noise) against the fp64 run AND <= max(1e-4, noise) against the fp32 run: as close to
+                    fp64 as the reference's own fp32 run, and inside that run's noise envelope around it (measured: 5.55e-3
+                    from fp64, 2.1e-3 from fp32 — both fp32 pipelines share the fp32 kNN graph, which is where they part from fp64)
+      loss          <= max(1e-5 relative, noise) against the fp64 run
+      gradients     L2 norm of every parameter gradient within 2 % of the reference's fp32 value, committed subsamples within
+                    5 % of the tensor's max-abs with at most 2 % of the entries beyond 2 %  (no fp64 gradient yardstick exists
+                    here; at N = 512, where one does, the reference's fp32-vs-fp64 gradient deviation reaches 1e-2 of the max.
+                    Measured: the worst tensor is the first layer's 64-entry bn1_lpd.weight at 1.4e-2 / norm 0.8 %)."""
+    g = golden("c3_train_step_n4096_b2")
+    ops.set_precision("fp32")
+    model = build_train(4096)
+    x = synth.clouds(44, 4096)
+    out, loss = run_step(model, x, 2)
+    out = out.detach().cpu().numpy()
+    noise = float(np.abs(g["out"] - g["out64"]).max())
+    err64, err32 = float(np.abs(out - g["out64"]).max()), float(np.abs(out - g["out"]).max())
+    print(f"\n[c3 full size] descriptors: vs ref fp64 {err64:.3e}, vs ref fp32 {err32:.3e}; reference fp32-vs-fp64 {noise:.3e}")
+    assert err64 <= max(1e-4, 1.05 * noise) and err32 <= max(1e-4, noise), \
+        f"train-mode descriptors: {err64:.3e} from the fp64 reference, {err32:.3e} from its fp32 run (reference's own fp32-vs-fp64: {noise:.3e})"
+    ref_loss, ref_loss64 = float(g["loss"]), float(g["loss64"])
+    lerr = abs(float(loss.detach()) - ref_loss64)
+    print(f"[c3 full size] loss {float(loss.detach()):.6f}: vs ref fp64 {lerr / ref_loss64:.3e} rel; reference fp32-vs-fp64 {abs(ref_loss - ref_loss64) / ref_loss64:.3e}")
+    assert lerr <= max(1e-5 * abs(ref_loss64), abs(ref_loss - ref_loss64)), f"loss {float(loss.detach())} vs fp64 {ref_loss64} (fp32 {ref_loss})"
+    bad, worst = {}, (0.0, 0.0, 0.0)
+    for key, p in model.named_parameters():
+        assert p.grad is not None, f"no gradient for {key}"
+        ref = g["grad." + key]
+        got = subsample(p.grad)
+        scale = max(np.abs(ref).max(), 1e-12)
+        err = np.abs(got - ref) / scale
+        gn, rn = float(p.grad.double().norm()), float(g["gnorm." + key])
+        worst = (max(worst[0], float(err.max())), max(worst[1], float((err > 2e-2).mean())), max(worst[2], abs(gn - rn) / rn))
+        if err.max() > 5e-2 or (err > 2e-2).mean() > 2e-2 or abs(gn - rn) > 2e-2 * rn:
+            bad[key] = (float(err.max()), float((err > 2e-2).mean()), abs(gn - rn) / rn)
+    print(f"[c3 full size] gradients: worst max-rel {worst[0]:.3e}, worst share beyond 2e-2 {worst[1]:.3e}, worst norm rel {worst[2]:.3e}")
+    assert not bad, f"gradient mismatch: {bad}"
+    sd = model.state_dict()
+    for key in g.files:
+        if key.startswith("after."):
+            assert np.allclose(sd[key[6:]].cpu().numpy(), g[key], rtol=1e-3, atol=1e-5), f"{key[6:]} after one train step"
+
+
 def test_adam_matches_torch_semantics(cuda):
     """lpd_adam against a numpy restatement of torch.optim.Adam (defaults, train_pointnetvlad.py:57)"""
     rng = np.random.default_rng(5)
@@ -189,6 +239,8 @@ def test_training_step_tf32_mode_close_to_fp32(cuda, golden):
     ("train_step_pointnet_ft_n256", dict(featnet="pointnet", feature_transform=True), 1234),
     ("train_step_lpdnet_tnets_n256", dict(featnet="lpdnet", feature_transform=True, xyz_trans=True), 1234),
     ("train_step_lpdnetorigin_tnets_n256", dict(featnet="lpdnetorigin", feature_transform=True, xyz_trans=True), 1234),
+    ("train_step_lpdnet_mfea_n256", dict(featnet="lpdnet", _mfea=dict(t3d=False)), 1234),
+    ("train_step_lpdnet_mfea_t3d_n256", dict(featnet="lpdnet", _mfea=dict(t3d=True)), 1234),
 ])
 def test_training_step_other_featnets_match_reference_autograd(cuda, golden, name, kw, seed):
     """train-mode forward + backward of the CLI default featnet (lpdnetorigin), PointNetVLAD (pointnet, with and without the
@@ -206,17 +258,28 @@ def test_training_step_other_featnets_match_reference_autograd(cuda, golden, nam
       tensors (oracle/gen_golden.py::_patch_batchnorm2d_w1); the forward is identical."""
     g = golden(name)
     ops.set_precision("fp32")
-    tnets = bool(kw.get("xyz_trans"))
-    model = PNV.PointNetVlad(num_points=256, emb_dims=1024, **kw)
+    mfea = kw.get("_mfea")
+    tnets = bool(kw.get("xyz_trans")) or bool(mfea and mfea["t3d"])
+    model = PNV.PointNetVlad(num_points=256, emb_dims=1024, **{k: v for k, v in kw.items() if not k.startswith("_")})
+    if mfea is not None:
+        # use_mFea (8-d input, reference lpdnet_model.py:215-222): PointNetVlad never enables it (:248), so the feature net
+        # is swapped in after construction, exactly as the golden generator does with the reference
+        from lpdnet_b200.util.lpdnet_model import LPDNet
+        model.emb_nn = LPDNet(emb_dims=1024, use_mFea=True, tfea=False, **mfea)
     model.load_state_dict(synth.synthetic_state_dict(model))
     model = model.cuda().train()
-    out, loss = run_step(model, synth.clouds(22, 256, seed=seed), 1)
+    out, loss = run_step(model, synth.clouds(22, 256, seed=seed, dims=8 if mfea is not None else 3), 1)
     out_noise = np.abs(g["out"] - g["out64"]).max()
     assert np.abs(out.detach().cpu().numpy() - g["out"]).max() <= max(1e-4, 1.5 * out_noise)
     ref_loss, ref_loss64 = float(g["loss"]), float(g["loss64"])
     # 1e-5 relative is the bar of the lpdnet C3 configuration (met in the test above); these secondary configurations get 3e-5
     assert abs(float(loss.detach()) - ref_loss) <= max(3e-5 * abs(ref_loss), 3.0 * abs(ref_loss - ref_loss64))
     floor_e, floor_n = (5e-2, 2e-2) if tnets else (5e-4, 5e-4)
+    if mfea is not None and not tnets:
+        # 8-d input: conv1 sums 8 products per channel in another order than the reference's conv1d, and the loss (22.5, far
+        # above the margins) weights every descriptor; two tensors sit at 0.5e-3 / 1.1e-3 of their max-abs (isolated entries,
+        # L2 norms agree to 6e-6): near-tie neighbour flips of the feature-space kNN, the same effect as in the T-Net cases
+        floor_e = 2e-3
     gmax = max(float(g[k]) for k in g.files if k.startswith("gnorm64."))
     bad = {}
     for key, p in model.named_parameters():
