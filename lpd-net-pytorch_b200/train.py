@@ -38,13 +38,21 @@ def dgrad(dz, lddz, w, rows, N, K, out=None, ldc=None, accumulate=False, tf32_ok
 # layer records
 # ----------------------------------------------------------------------------------------------------------------------
 class _Grads:
-    """parameter -> gradient tensor (in the parameter's own shape); accumulates when a parameter is hit twice"""
+    """parameter -> gradient tensor (in the parameter's own shape); accumulates when a parameter is hit twice.
+    A gradient declared `final` (no later contribution in this backward) is offered to the parameter's gradient sink, if it
+    has one: lpdnet_b200.optim.Adam registers itself on its large parameters so that their data-parallel all-reduce starts
+    while the rest of the backward is still running."""
 
     def __init__(self):
         self.by_param = {}
 
-    def add(self, param: torch.Tensor, g: torch.Tensor):
+    def add(self, param: torch.Tensor, g: torch.Tensor, final: bool = False):
         g = g.reshape(param.shape)
+        if final and param not in self.by_param:
+            sink = getattr(param, "_lpd_grad_sink", None)
+            sink = sink() if sink is not None else None
+            if sink is not None and sink.grad_ready(param, g.contiguous()):
+                return                                       # the optimizer owns it now: autograd gets None for this parameter
         cur = self.by_param.get(param)
         if cur is None:
             self.by_param[param] = g.contiguous()
@@ -588,7 +596,9 @@ class NetVLADTrain:
         dhpre = self.bn_h.bwd(dh, O, grads)
         wh = nv.hidden1_weights.detach()
         KD = D * K
-        grads.add(nv.hidden1_weights, ops.gemm(self.v, dhpre, a_layout=A_KM, b_layout=B_KN, M=KD, N=O, K=B, lda=KD, ldb=O))
+        # the 64 MiB hidden-projection gradient is 95 % of all gradient bytes and the FIRST one to be complete: final -> its
+        # NCCL all-reduce overlaps the whole rest of the backward (optim.Adam.grad_ready)
+        grads.add(nv.hidden1_weights, ops.gemm(self.v, dhpre, a_layout=A_KM, b_layout=B_KN, M=KD, N=O, K=B, lda=KD, ldb=O), final=True)
         dv = ops.gemm(dhpre, wh, a_layout=A_MK, b_layout=B_NK, M=B, N=KD, K=O, lda=O, ldb=O)   # [B, D*K]
         wc2 = nv.cluster_weights2.detach()[0].contiguous()
         dvraw, dasum, dwc2 = ops.netvlad_finish_bwd(dv, self.v, wc2, self.asum, self.n1, self.n2, B, D, K)
