@@ -168,6 +168,21 @@ int lpd_gemm_tf32_ex(const float* A, int lda, const float* B, int ldb, float* C,
 int lpd_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long strideC,
                      int M, int N, int K, int batch, void* stream);
 
+/* FP16-operand forms of the tensor-core GEMMs ("f16" precision mode of the eval path; csrc/gemm_tc.cu): operands are fp16
+ * matrices (rounded to nearest by the producing kernel's epilogue or by lpd_f32_to_f16), products accumulate in fp32 on
+ * tcgen05 kind::f16.  fp16 keeps 11 significant bits under round-to-nearest where kind::tf32 TRUNCATES fp32 operands to 10
+ * (measured on the reference goldens: 1e-5 vs 5e-5 max-abs descriptor error), at twice the tensor rate and half the bytes.
+ * Out-of-range results saturate to +-65504 (cvt.rn.satfinite) when the output is fp16.
+ *   lpd_gemm_f16:     C[m][n] = act(scale[n] * sum_k A[m][k] W[n][k] + shift[n]);  A [M][lda], W [N][ldw] fp16 (lda, ldw % 8 == 0),
+ *                     C fp32 (out_half == 0) or fp16 (out_half != 0) with leading dimension ldc (% 4 == 0) in elements.
+ *   lpd_gemm_f16_tn:  C[z][m][n] = sum_{k<K} A[z*K+k][m] B[z*K+k][n]  (fp16 operands, fp32 C; batch > 1 needs K % 64 == 0).
+ *   lpd_f32_to_f16:   y[r][c] = fp16(x[r][c]) for a [rows][cols] matrix (weights, once per parameter version). */
+int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_half,
+                 int M, int N, int K, const float* scale, const float* shift, int act, float slope, void* stream);
+int lpd_gemm_f16_tn(const void* A, int lda, const void* B, int ldb, float* C, int ldc, long long strideC,
+                    int M, int N, int K, int batch, void* stream);
+int lpd_f32_to_f16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols, void* stream);
+
 /* Fused input layers of the LPD-Net feature nets (lpdnet_model.py:231-232, :86-87), strict fp32, one pass:
  *     out[m][:] = act(s2 * (W2 . act(s1 * (W1 . x[m][0..D)) + t1)) + t2),   W1 [64][D], W2 [64][64], D <= 8
  * x [M][ldx], out [M][ldo]; act in {NONE, RELU, LEAKY with 0 <= slope <= 1}. */
@@ -208,7 +223,10 @@ int lpd_edgeconv_dg(const float* p, int ldp, const float* q, int ldq,
 
 /* Same contract as lpd_edgeconv_dg with the second edge layer on the tensor cores (tcgen05 kind::tf32, the
  * activated first-layer edge rows are written by the gathering warps straight into the UMMA shared-memory
- * layout; fp32 first layer, TF32 second layer, fp32 accumulation).  Requires sm_100. */
+ * layout; fp32 first layer, TF32 second layer, fp32 accumulation).  Requires sm_100.
+ * s1 == t1 == NULL selects the PRE-SCALED form for the reference's own shape (k == 20, C1 == C2 == 128): the caller has folded the
+ * first layer's BatchNorm into the projections (p = s1 * Wn f, q = s1 * Wc f + t1, e.g. in the projection GEMM's epilogue), so
+ * y1 = act(p_j + q_i); csrc/edge_tc20.cu. */
 int lpd_edgeconv_dg_tf32(const float* p, int ldp, const float* q, int ldq,
                          const int32_t* idx, int B, int N, int k, int C1, int C2,
                          const float* s1, const float* t1, const float* w2,

@@ -277,6 +277,9 @@ static int dg_tc_launch(const CUtensorMap& tw, DgTcParams P, cudaStream_t st) {
     return LPD_OK;
 }
 
+int dg20_tc_run(const float* p, int ldp, const float* q, int ldq, const int32_t* idx, int B, int N, const float* w2,
+                const float* s2, const float* t2, float neg_slope, float* x1, int ld1, float* x2, int ld2, cudaStream_t st);
+
 }  // namespace tc
 }  // namespace lpd
 
@@ -286,7 +289,8 @@ extern "C" int lpd_edgeconv_dg_tf32(const float* p, int ldp, const float* q, int
                                     const float* s2, const float* t2, int act, float slope,
                                     float* x1, int ld1, float* x2, int ld2, void* stream) {
     using namespace lpd;
-    LPD_REQUIRE(p && q && idx && s1 && t1 && w2 && s2 && t2 && x2);
+    LPD_REQUIRE(p && q && idx && w2 && s2 && t2 && x2);
+    LPD_REQUIRE((s1 && t1) || (!s1 && !t1 && k == 20 && C1 == 128 && C2 == 128));   // pre-scaled first layer: specialised kernel only
     LPD_REQUIRE(B >= 1 && N >= 1 && k >= 1 && k <= 32 && k <= N);
     LPD_REQUIRE((C1 == 128 && C2 == 128) || (C1 == 64 && C2 == 64));
     LPD_REQUIRE(ldp % 4 == 0 && ldq % 4 == 0 && (!x1 || ld1 % 4 == 0));
@@ -298,6 +302,9 @@ extern "C" int lpd_edgeconv_dg_tf32(const float* p, int ldp, const float* q, int
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return LPD_EUNSUPPORTED;
+    if (!s1)    // k = 20, 128 channels, first-layer BatchNorm already applied by the projection GEMM (edge_tc20.cu)
+        return tc::dg20_tc_run(p, ldp, q, ldq, idx, B, N, w2, s2, t2, act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope),
+                               x1, ld1, x2, ld2, as_stream(stream));
     tc::DgTcParams P;
     P.p = p; P.q = q; P.idx = idx; P.s1 = s1; P.t1 = t1; P.s2 = s2; P.t2 = t2; P.x1 = x1; P.x2 = x2;
     P.ldp = ldp; P.ldq = ldq; P.ld1 = ld1; P.ld2 = ld2; P.total_pts = (long long)B * N; P.N = N; P.k = k; P.C2 = C2;

@@ -1,0 +1,255 @@
+// EdgeConv double layer on the tensor cores, specialised for the reference's own shape: k = 20 neighbours, C1 = C2 = 128
+// (LPDNet convDG1 + max + convDG2 + max, reference util/lpdnet_model.py:246-252), first layer PRE-SCALED:
+//     the folded BatchNorm of the first edge layer is applied by the per-point projection GEMM's epilogue
+//     (p' = s1 * Wn f, q' = s1 * Wc f + t1), so an activated edge row is just  y1 = act(p'_j + q'_i).
+// Same operand roles as edge_tc.cu (A = W2 resident in shared memory, B = the activated edge rows, one TMEM lane per output
+// channel, the k edges of a point in consecutive accumulator columns).  What changes is the producer side, which bounded the
+// generic kernel (54 instructions per gathered row, 60 % of all instructions, tensor pipe 19 % active):
+//   * every point owns a 24-row slot of the 128-row edge tile (5 points per tile): slot bases are multiples of 8 rows, so the
+//     128B-swizzle term of a row's store address depends on the neighbour number only and, with k a compile-time constant,
+//     every store offset inside the unrolled loops is an immediate; rows 20-23 of a slot stay zero;
+//   * no per-row predicates (k is known), no first-layer multiply-add (pre-scaled);
+//   * TWO producer warps per point, each owning one half of the channels (16 lanes x float4 per row, two rows per warp
+//     iteration): 20 producer warps in two groups of 10 (one group per shared-memory / TMEM stage) + 4 epilogue warps.
+#include "tc_common.cuh"
+
+namespace lpd {
+namespace tc {
+
+constexpr int D20_K = 20, D20_SLOT = 24, D20_PTS = 5, D20_C = 128;
+constexpr int D20_EPI_WARPS = 4, D20_GROUP_WARPS = 2 * D20_PTS, D20_PROD_WARPS = 2 * D20_GROUP_WARPS;
+constexpr int D20_THREADS = 32 * (D20_EPI_WARPS + D20_PROD_WARPS);
+constexpr int D20_ALLOC_WARP = D20_EPI_WARPS;
+constexpr int D20_ACC_STRIDE = 256;
+constexpr uint32_t D20_KB_BYTES = 128 * 128;           // one 32-channel k-block of a 128-row operand tile
+constexpr uint32_t D20_OP_BYTES = 4 * D20_KB_BYTES;    // a whole operand tile: 64 KB
+
+struct Dg20Params {
+    const float* p; const float* q; const int* idx;
+    const float* s2; const float* t2;
+    float* x1; float* x2;
+    int ldp, ldq, ld1, ld2;
+    long long total_pts; int N;
+    float neg_slope;                  // act(v) = max(v, v * neg_slope)
+    long long num_tiles;
+};
+
+__global__ void __launch_bounds__(D20_THREADS, 1)
+edgeconv_dg20_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20Params P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* w_s = smem;
+    uint8_t* y_s = smem + D20_OP_BYTES;               // [2][OP_BYTES]
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + 3 * D20_OP_BYTES);
+    uint64_t* yfull = wfull + 1;
+    uint64_t* yempty = yfull + 2;
+    uint64_t* tfull = yempty + 2;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // zero both edge stages once: rows 20-23 of every slot and rows 120-127 are never written again
+    for (uint32_t i = threadIdx.x; i < 2 * D20_OP_BYTES / 16; i += D20_THREADS)
+        reinterpret_cast<uint4*>(y_s)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    if (warp == D20_ALLOC_WARP) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w2)) : "memory");
+            mbar_init(wfull, 1);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&yfull[s], D20_GROUP_WARPS);
+                mbar_init(&yempty[s], 1);
+                mbar_init(&tfull[s], 1);
+                mbar_init(&tempty[s], D20_EPI_WARPS);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= D20_EPI_WARPS) {
+        // ------------------------------ producers ------------------------------
+        const int pwarp = warp - D20_EPI_WARPS;
+        const int grp = pwarp / D20_GROUP_WARPS;                   // = the shared-memory / TMEM stage this warp fills
+        const int gw = pwarp % D20_GROUP_WARPS;
+        const int pl = gw >> 1, chalf = gw & 1;                    // point slot inside the tile, channel half
+        const bool issuer = gw == 0;
+        if (warp == D20_ALLOC_WARP && lane == 0) {
+            mbar_expect_tx(wfull, D20_OP_BYTES);
+            for (int kb2 = 0; kb2 < 4; ++kb2) tma_load_2d(w_s + kb2 * D20_KB_BYTES, &tmap_w2, wfull, kb2 * 32, 0);
+        }
+        constexpr uint32_t idesc = make_idesc(128, 128);
+        const uint32_t w_addr = smem_u32(w_s);
+        bool w_ready = false;
+        const int sr = lane >> 4, lc = lane & 15;                  // row of the pair this lane works on, float4 index inside the half row
+        const int ch = chalf * 64 + lc * 4;                        // first of this lane's 4 channels
+        const int kb = ch >> 5, chunk = (ch >> 2) & 7;             // k-block and 16-byte chunk of those channels
+        // store address of edge row m of this point:  slot base + m * 128 + ((chunk ^ (m & 7)) << 4), m = 2 i + sr:
+        // (m & 7) = ((2 i) & 7) | sr, so chunk ^ (m & 7) = (chunk ^ sr) ^ ((2 i) & 7): four per-lane offsets, the rest immediates
+        uint32_t xo[4];
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) xo[b2] = (uint32_t)(((chunk ^ sr) ^ (2 * b2)) << 4);
+        uint8_t* ybase = y_s + grp * D20_OP_BYTES + kb * D20_KB_BYTES + (pl * D20_SLOT + sr) * 128;
+        const long long tstep = 2LL * gridDim.x;
+        long long t = blockIdx.x + (long long)grp * gridDim.x;
+        // software pipeline: the neighbour list and centre row of the NEXT tile's point are requested before waiting for the stage
+        int nj = 0;
+        float4 nq = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto prefetch = [&](long long tile) {
+            const long long pt = tile * D20_PTS + pl;
+            if (tile < P.num_tiles && pt < P.total_pts) {
+                nj = (lane < D20_K) ? __ldg(P.idx + pt * D20_K + lane) : 0;
+                nq = __ldg(reinterpret_cast<const float4*>(P.q + pt * P.ldq + ch));
+            }
+        };
+        prefetch(t);
+        const float slope = P.neg_slope;
+        for (uint32_t it = 0; t < P.num_tiles; t += tstep, ++it) {
+            const uint32_t ph = it & 1;
+            const int myj = nj;
+            const float4 qv = nq;
+            const long long pt = t * D20_PTS + pl;
+            prefetch(t + tstep);
+            mbar_wait(&yempty[grp], ph ^ 1);
+            if (pt < P.total_pts) {
+                const float* pbase = P.p + (pt / P.N) * P.N * P.ldp + ch;      // row address = one 32-bit multiply-add on this base
+                float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                                  // 2 x 5 row pairs: 5 gathers in flight per lane
+                    float4 pv[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) {
+                        const int j = __shfl_sync(kFull, myj, 2 * (5 * h + u) + sr);
+                        pv[u] = __ldg(reinterpret_cast<const float4*>(pbase + (unsigned)(j * P.ldp)));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) {
+                        const int i2 = 5 * h + u;                               // row pair: rows 2 i2 and 2 i2 + 1
+                        best.x = fmaxf(best.x, pv[u].x); best.y = fmaxf(best.y, pv[u].y);
+                        best.z = fmaxf(best.z, pv[u].z); best.w = fmaxf(best.w, pv[u].w);
+                        float4 y;
+                        y.x = pv[u].x + qv.x; y.y = pv[u].y + qv.y; y.z = pv[u].z + qv.z; y.w = pv[u].w + qv.w;
+                        y.x = fmaxf(y.x, y.x * slope); y.y = fmaxf(y.y, y.y * slope);
+                        y.z = fmaxf(y.z, y.z * slope); y.w = fmaxf(y.w, y.w * slope);
+                        *reinterpret_cast<float4*>(ybase + i2 * 256 + xo[i2 & 3]) = y;
+                    }
+                }
+                if (P.x1) {
+                    // max_m act(p'_m + q') = act(max_m p'_m + q'): the activation is monotone
+                    best.x = fmaxf(best.x, __shfl_xor_sync(kFull, best.x, 16)); best.y = fmaxf(best.y, __shfl_xor_sync(kFull, best.y, 16));
+                    best.z = fmaxf(best.z, __shfl_xor_sync(kFull, best.z, 16)); best.w = fmaxf(best.w, __shfl_xor_sync(kFull, best.w, 16));
+                    if (sr == 0) {
+                        float4 o;
+                        o.x = best.x + qv.x; o.y = best.y + qv.y; o.z = best.z + qv.z; o.w = best.w + qv.w;
+                        o.x = fmaxf(o.x, o.x * slope); o.y = fmaxf(o.y, o.y * slope); o.z = fmaxf(o.z, o.z * slope); o.w = fmaxf(o.w, o.w * slope);
+                        *reinterpret_cast<float4*>(P.x1 + pt * P.ld1 + ch) = o;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&yfull[grp]);
+            if (issuer) {   // warp-uniform: the whole warp runs the issue sequence, elect.sync picks the lane (see tc_common.cuh)
+                if (!w_ready) { mbar_wait(wfull, 0); w_ready = true; }
+                mbar_wait(&tempty[grp], ph ^ 1);
+                mbar_wait(&yfull[grp], ph);
+                tc_fence_after();
+                const uint32_t y_addr = smem_u32(y_s + grp * D20_OP_BYTES);
+#pragma unroll
+                for (int kb2 = 0; kb2 < 4; ++kb2) {
+                    const uint64_t da = make_smem_desc(w_addr + kb2 * D20_KB_BYTES), db = make_smem_desc(y_addr + kb2 * D20_KB_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        tc_mma_tf32_e(tmem_base + grp * D20_ACC_STRIDE, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc,
+                                      (kb2 | ks) != 0 ? 1u : 0u);
+                }
+                tc_commit_e(&yempty[grp]);
+                tc_commit_e(&tfull[grp]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------ epilogue ------------------------------
+        // BN (scale s2, shift t2) and the activation are monotone per channel, and a lane owns ONE channel, so
+        //     max_m act(s2 * d_m + t2) = act(s2 * ext_m d_m + t2),  ext = max if s2 >= 0 else min            (exact in fp32)
+        const int ch = warp * 32 + lane;               // output channel = TMEM lane
+        const float s2 = __ldg(P.s2 + ch), t2 = __ldg(P.t2 + ch);
+        long long t = blockIdx.x;
+        for (uint32_t it = 0; t < P.num_tiles; t += gridDim.x, ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            mbar_wait(&tfull[s], ph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int pl = 0; pl < D20_PTS; ++pl) {
+                const long long pt = t * D20_PTS + pl;
+                if (pt >= P.total_pts) break;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + s * D20_ACC_STRIDE + pl * D20_SLOT;
+                uint32_t r[20];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(taddr + 16));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float a4[4], b4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { a4[u] = __uint_as_float(r[u]); b4[u] = a4[u]; }
+#pragma unroll
+                for (int j = 4; j < 20; j += 2) {
+                    const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+                    a4[(j >> 1) & 3] = fmaxf(fmaxf(a4[(j >> 1) & 3], v0), v1);
+                    b4[(j >> 1) & 3] = fminf(fminf(b4[(j >> 1) & 3], v0), v1);
+                }
+                const float mx = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));
+                const float mn = fminf(fminf(b4[0], b4[1]), fminf(b4[2], b4[3]));
+                float v = fmaf(s2, s2 >= 0.f ? mx : mn, t2);
+                v = fmaxf(v, v * P.neg_slope);
+                P.x2[pt * P.ld2 + ch] = v;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[s]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == D20_ALLOC_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// called by lpd_edgeconv_dg_tf32 (edge_tc.cu) for k == 20, C1 == C2 == 128, s1 == t1 == NULL
+int dg20_tc_run(const float* p, int ldp, const float* q, int ldq, const int32_t* idx, int B, int N, const float* w2,
+                const float* s2, const float* t2, float neg_slope, float* x1, int ld1, float* x2, int ld2, cudaStream_t st) {
+    Dg20Params P;
+    P.p = p; P.q = q; P.idx = idx; P.s2 = s2; P.t2 = t2; P.x1 = x1; P.x2 = x2;
+    P.ldp = ldp; P.ldq = ldq; P.ld1 = ld1; P.ld2 = ld2; P.total_pts = (long long)B * N; P.N = N;
+    P.neg_slope = neg_slope;
+    P.num_tiles = (P.total_pts + D20_PTS - 1) / D20_PTS;
+    CUtensorMap tw;
+    int rc = make_tmap(&tw, w2, D20_C, D20_C, D20_C, 128);
+    if (rc != LPD_OK) return rc;
+    constexpr size_t smem = 3 * (size_t)D20_OP_BYTES + 256;
+    LPD_CUDA_CHECK(allow_smem(edgeconv_dg20_tc_kernel, smem));
+    int dev = 0, sms = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)(P.num_tiles < sms ? P.num_tiles : sms);
+    edgeconv_dg20_tc_kernel<<<grid, D20_THREADS, smem, st>>>(tw, P);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+}  // namespace tc
+}  // namespace lpd

@@ -14,14 +14,20 @@
 //             32 columns, raw accumulators transposed through an XOR-swizzled 4 KB per-warp staging buffer, then
 //             affine + activation applied on the way out so that every st.global.v4 instruction writes four full
 //             128-byte lines.  (TMA stores were measured slower here: they queue behind the producer's prefetch.)
+//
+// The same kernel also runs with FP16 operands (kind::f16, fp32 accumulation; template parameter TIN = __half): 64 halves per
+// 128-byte shared-memory row, K = 16 per MMA — the byte geometry of the pipeline is unchanged — and can write its output as
+// fp16 (OUT_HALF).  That is the "f16" precision mode of the eval path: operands rounded to nearest fp16 (11 significant
+// bits, vs the 10-bit TRUNCATION kind::tf32 applies to fp32 operands), twice the tensor rate and half the operand bytes.
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace lpd {
 namespace tc {
 
 constexpr int BM = 128;      // UMMA M
-constexpr int BK = 32;       // fp32 elements per smem row = 128 bytes = one swizzle span
-constexpr int UMMA_K = 8;    // tf32
+constexpr int BK = 32;       // fp32 elements per smem row = 128 bytes = one swizzle span (fp16: 64 elements)
+constexpr int UMMA_K = 8;    // tf32 (fp16: 16) — 32 bytes of K per MMA either way
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
@@ -41,9 +47,37 @@ struct Params {
 //               operand tile (128B swizzle, 32-byte atom — the only MN-major layout kind::tf32 accepts) is a row of TMA boxes
 //               {32 floats, 32 k-rows}: 4-row atoms 512 B apart (SBO), 32-element MN groups one box = 4096 B apart (LBO);
 //               a K=8 MMA step advances the start address by two atoms (1024 B).
-template <int BN, int STAGES, bool TN>
+__device__ __forceinline__ void tc_mma_f16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// kind::f16, fp16 operands (format 0), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_h(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major fp16 operand tile built from TMA boxes {64 halves along M/N (128 B), 64 k-rows}, plain 128B swizzle: 8-k-row atoms
+// 1024 B apart (stride byte offset), 64-element M/N groups one box = 8192 B apart (leading byte offset)
+__device__ __forceinline__ uint64_t make_smem_desc_mn_h(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(8192 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+template <int BN, int STAGES, bool TN, typename TIN = float, bool OUT_HALF = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
+    constexpr bool HALF = sizeof(TIN) == 2;
+    constexpr int BKE = HALF ? 2 * BK : BK;              // K elements per 128-byte shared-memory row / per ring slot
+    constexpr int MNB = HALF ? 64 : 32;                  // TN: M/N elements per TMA box (128 bytes)
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two >= 32 for BN in {64,128,256})
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -56,7 +90,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_kb = (p.K + BKE - 1) / BKE;
     const int tiles_mn = p.tiles_m * p.tiles_n;
     const int num_tiles = tiles_mn * p.batch;
 
@@ -87,14 +121,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_expect_tx_e(&full[stage], STAGE_BYTES);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     if (TN) {
-                        const int k0 = z * p.K + kb * BK;
+                        const int k0 = z * p.K + kb * BKE;        // boxes of {MNB elements, BKE k-rows}: 4096 B (fp32) / 8192 B (fp16)
 #pragma unroll
-                        for (int i = 0; i < BM / 32; ++i) tma_load_2d_e(sa + i * 4096, &tmap_a, &full[stage], m0 + i * 32, k0);
+                        for (int i = 0; i < BM / MNB; ++i) tma_load_2d_e(sa + i * (MNB * 128), &tmap_a, &full[stage], m0 + i * MNB, k0);
 #pragma unroll
-                        for (int i = 0; i < BN / 32; ++i) tma_load_2d_e(sa + A_BYTES + i * 4096, &tmap_b, &full[stage], n0 + i * 32, k0);
+                        for (int i = 0; i < BN / MNB; ++i) tma_load_2d_e(sa + A_BYTES + i * (MNB * 128), &tmap_b, &full[stage], n0 + i * MNB, k0);
                     } else {
-                        tma_load_2d_e(sa, &tmap_a, &full[stage], kb * BK, z * p.bM + m0);
-                        tma_load_2d_e(sa + A_BYTES, &tmap_b, &full[stage], kb * BK, z * p.bN + n0);
+                        tma_load_2d_e(sa, &tmap_a, &full[stage], kb * BKE, z * p.bM + m0);
+                        tma_load_2d_e(sa + A_BYTES, &tmap_b, &full[stage], kb * BKE, z * p.bN + n0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -102,7 +136,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp == 1) {
         {   // whole warp, elect.sync picks the issuing lane (see tc_common.cuh)
-            constexpr uint32_t idesc = make_idesc(BM, BN) | (TN ? ((1u << 15) | (1u << 16)) : 0u);   // a_major / b_major = MN
+            constexpr uint32_t idesc = (HALF ? make_idesc_h(BM, BN) : make_idesc(BM, BN)) | (TN ? ((1u << 15) | (1u << 16)) : 0u);   // a_major / b_major = MN
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -113,7 +147,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    if (TN) {
+                    if (TN && HALF) {
+                        const uint64_t da = make_smem_desc_mn_h(sa), db = make_smem_desc_mn_h(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)                // 16 k-rows (2048 B) per K=16 step, 64 k-rows per slot
+                            tc_mma_f16_e(tmem_d, da + (uint64_t)(k * 2048 >> 4), db + (uint64_t)(k * 2048 >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+                    } else if (TN) {
                         const uint64_t da = make_smem_desc_mn(sa), db = make_smem_desc_mn(sa + A_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)      // 8 k-rows (1024 B) per K=8 step
@@ -122,9 +161,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     } else {
                         const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            tc_mma_tf32_e(tmem_d, da + (uint64_t)(k * UMMA_K * 4 >> 4), db + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
-                                        (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {    // 32 bytes of K per MMA: 8 tf32 or 16 fp16 elements
+                            if (HALF) tc_mma_f16_e(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                            else tc_mma_tf32_e(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     tc_commit_e(&empty[stage]);           // slot reusable once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -178,7 +218,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
                     if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
                 }
-                float* gcol = p.C + (TN ? (size_t)z * p.strideC : (size_t)z * p.bM * p.ldc) + (size_t)row0 * p.ldc + col;
+                const size_t goff = (TN ? (size_t)z * p.strideC : (size_t)z * p.bM * p.ldc) + (size_t)row0 * p.ldc + col;
+                float* gcol = p.C + goff;
+                __half* hcol = reinterpret_cast<__half*>(p.C) + goff;          // OUT_HALF: C is an fp16 matrix (ldc in halves)
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int rr = it * 4 + rsub;
@@ -187,9 +229,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     v.x = fmaxf(v.x, v.x * p.neg_slope); v.y = fmaxf(v.y, v.y * p.neg_slope);
                     v.z = fmaxf(v.z, v.z * p.neg_slope); v.w = fmaxf(v.w, v.w * p.neg_slope);
                     if (col_ok && row0 + rr < p.M) {
-                        float4* dstp = reinterpret_cast<float4*>(gcol + (size_t)rr * p.ldc);
-                        if (!TN && p.accumulate) { const float4 o = oldc[it]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                        *dstp = v;
+                        if (OUT_HALF) {
+                            __half2 h0, h1;                                      // saturating: out-of-range values become +-65504, not inf
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(*reinterpret_cast<uint32_t*>(&h0)) : "f"(v.y), "f"(v.x));
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(*reinterpret_cast<uint32_t*>(&h1)) : "f"(v.w), "f"(v.z));
+                            *reinterpret_cast<uint2*>(hcol + (size_t)rr * p.ldc) =
+                                make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                        } else {
+                            float4* dstp = reinterpret_cast<float4*>(gcol + (size_t)rr * p.ldc);
+                            if (!TN && p.accumulate) { const float4 o = oldc[it]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                            *dstp = v;
+                        }
                     }
                 }
                 __syncwarp();                            // staging buffer is rewritten by the next chunk
@@ -208,10 +258,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 }
 
-template <int BN, int STAGES, bool TN = false>
+template <int BN, int STAGES, bool TN = false, typename TIN = float, bool OUT_HALF = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + EPI_WARPS * 32 * 32 * 4 + 256;
-    LPD_CUDA_CHECK(allow_smem(gemm_tf32_kernel<BN, STAGES, TN>, smem));
+    LPD_CUDA_CHECK(allow_smem(gemm_tf32_kernel<BN, STAGES, TN, TIN, OUT_HALF>, smem));
     int dev = 0, sms = 0;
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -219,13 +269,112 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaSt
     p.tiles_n = ceil_div(p.N, BN);
     const long long tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_tf32_kernel<BN, STAGES, TN><<<grid, THREADS, smem, st>>>(ta, tb, p);
+    gemm_tf32_kernel<BN, STAGES, TN, TIN, OUT_HALF><<<grid, THREADS, smem, st>>>(ta, tb, p);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }
 
+// 2-D fp16 tensor [rows][cols] with leading dimension ld (elements), box = [box_rows][64 cols = 128 B], 128B swizzle
+static int make_tmap_h(CUtensorMap* m, const void* base, long long rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled entry point not found"); return LPD_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled (fp16) failed: CUresult %d", (int)r); return LPD_ECUDA; }
+    return LPD_OK;
+}
+
+__global__ void __launch_bounds__(256)
+f32_to_f16_kernel(const float* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, long long rows, int cols) {
+    const long long total = rows * cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / cols;
+        const int c = (int)(e % cols);
+        y[r * ldy + c] = __float2half_rn(x[r * ldx + c]);
+    }
+}
+
 }  // namespace tc
 }  // namespace lpd
+
+extern "C" int lpd_f32_to_f16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(x && y && rows >= 1 && cols >= 1 && ldx >= cols && ldy >= cols);
+    const long long total = rows * cols;
+    const long long blocks = (total + 255) / 256;
+    tc::f32_to_f16_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, as_stream(stream)>>>(
+        x, ldx, reinterpret_cast<__half*>(y), ldy, rows, cols);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+extern "C" int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_half,
+                            int M, int N, int K, const float* scale, const float* shift, int act, float slope, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(A && W && C && M >= 1 && N >= 1 && K >= 1);
+    LPD_REQUIRE(lda >= K && ldw >= K && ldc >= N);
+    LPD_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0 && (ldc % 4) == 0);          // 16-byte global strides (TMA), vector stores
+    LPD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0);
+    LPD_REQUIRE((N % 4) == 0);
+    LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || (act == LPD_ACT_LEAKY && slope >= 0.f && slope <= 1.f));
+    int dev = 0, major = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return LPD_EUNSUPPORTED;
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    CUtensorMap ta, tb;
+    int rc = tc::make_tmap_h(&ta, A, M, K, lda, tc::BM);
+    if (rc != LPD_OK) return rc;
+    rc = tc::make_tmap_h(&tb, W, N, K, ldw, BN);
+    if (rc != LPD_OK) return rc;
+    tc::Params p;
+    p.C = reinterpret_cast<float*>(C); p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = scale; p.shift = shift;
+    p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
+    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0;
+    cudaStream_t st = as_stream(stream);
+    if (out_half) {
+        if (BN == 64) return tc::launch<64, 8, false, __half, true>(ta, tb, p, st);
+        if (BN == 128) return tc::launch<128, 6, false, __half, true>(ta, tb, p, st);
+        return tc::launch<256, 4, false, __half, true>(ta, tb, p, st);
+    }
+    if (BN == 64) return tc::launch<64, 8, false, __half, false>(ta, tb, p, st);
+    if (BN == 128) return tc::launch<128, 6, false, __half, false>(ta, tb, p, st);
+    return tc::launch<256, 4, false, __half, false>(ta, tb, p, st);
+}
+
+extern "C" int lpd_gemm_f16_tn(const void* A, int lda, const void* B, int ldb, float* C, int ldc, long long strideC,
+                               int M, int N, int K, int batch, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1 && batch >= 1);
+    LPD_REQUIRE(lda >= M && ldb >= N && ldc >= N);
+    LPD_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && (ldc % 4) == 0 && (strideC % 4) == 0);
+    LPD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0);
+    LPD_REQUIRE((N % 4) == 0);
+    LPD_REQUIRE(batch == 1 || (K % 64) == 0);              // a slice's k-blocks must not run into the next slice
+    int dev = 0, major = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return LPD_EUNSUPPORTED;
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    const long long rows = (long long)K * batch;
+    CUtensorMap ta, tb;
+    int rc = tc::make_tmap_h(&ta, A, rows, M, lda, 64);     // boxes {64 halves along M, 64 k-rows}
+    if (rc != LPD_OK) return rc;
+    rc = tc::make_tmap_h(&tb, B, rows, N, ldb, 64);
+    if (rc != LPD_OK) return rc;
+    tc::Params p;
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = nullptr; p.shift = nullptr; p.neg_slope = 1.f;
+    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = strideC; p.bM = p.bN = 0; p.accumulate = 0;
+    cudaStream_t st = as_stream(stream);
+    if (BN == 64) return tc::launch<64, 8, true, __half>(ta, tb, p, st);
+    if (BN == 128) return tc::launch<128, 6, true, __half>(ta, tb, p, st);
+    return tc::launch<256, 4, true, __half>(ta, tb, p, st);
+}
 
 extern "C" int lpd_gemm_tf32_ex(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                                 int M, int N, int K, int batch, int accumulate, const float* scale, const float* shift, int act,

@@ -247,6 +247,54 @@ def gemm_tf32_tn(A, Bm, *, M, N, K, lda, ldb, batch=1, out=None):
     return out
 
 
+def to_f16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, cols] (last dim contiguous) -> fp16 copy, rounded to nearest (lpd_f32_to_f16)"""
+    lib = _lib.load()
+    _f32(x, "x")
+    rows, cols = x.shape
+    y = torch.empty(rows, cols, device=x.device, dtype=torch.float16)
+    _call("lpd_f32_to_f16", 1, lib.lpd_f32_to_f16, x.data_ptr(), x.stride(0), y.data_ptr(), cols, rows, cols, _stream())
+    return y
+
+
+def _f16(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.float16:
+        raise _lib.LpdError(f"{name} must be a CUDA float16 tensor, got {t.dtype} on {t.device}")
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.LpdError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}")
+    return t
+
+
+def gemm_f16(A, W, *, M, N, K, lda=None, ldw=None, out=None, ldc=None, out_half=False, scale=None, shift=None, act=ACT_NONE, slope=0.0):
+    """out[m][n] = act(scale[n] * sum_k A[m][k] W[n][k] + shift[n]) with fp16 operands on the tensor cores (fp32 accumulate);
+    the output is fp32, or fp16 when out_half (or `out` is an fp16 tensor)."""
+    lib = _lib.load()
+    _f16(A, "A"), _f16(W, "W")
+    lda = K if lda is None else lda
+    ldw = K if ldw is None else ldw
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.float16 if out_half else torch.float32)
+        ldc = N
+    else:
+        out_half = out.dtype == torch.float16
+        if ldc is None:
+            ldc = out.stride(-2)
+    _call(f"lpd_gemm_f16[{M}x{N}x{K}]", 1, lib.lpd_gemm_f16, A.data_ptr(), lda, W.data_ptr(), ldw, out.data_ptr(), ldc, int(out_half),
+          M, N, K, _p(scale), _p(shift), act, float(slope), _stream())
+    return out
+
+
+def gemm_f16_tn(A, Bm, *, M, N, K, lda, ldb, batch=1, out=None):
+    """out[z][m][n] = sum_{k<K} A[z*K+k][m] * Bm[z*K+k][n], fp16 operands (rows = the contraction axis), fp32 out [batch, M, N]"""
+    lib = _lib.load()
+    _f16(A, "A"), _f16(Bm, "B")
+    if out is None:
+        out = torch.empty(batch, M, N, device=A.device, dtype=torch.float32)
+    _call(f"lpd_gemm_f16_tn[{M}x{N}x{K}x{batch}]", 1, lib.lpd_gemm_f16_tn, A.data_ptr(), lda, Bm.data_ptr(), ldb, out.data_ptr(), N,
+          M * N, M, N, K, batch, _stream())
+    return out
+
+
 def _tn_ok(A, Bm, M, N, K, lda, ldb, batch):
     return (_precision == "tf32" and M >= 64 and N >= 64 and N % 4 == 0 and lda % 4 == 0 and ldb % 4 == 0 and K >= 256
             and (batch == 1 or K % 32 == 0) and A.data_ptr() % 16 == 0 and Bm.data_ptr() % 16 == 0)
@@ -288,12 +336,15 @@ def edge_gather_ext(p, ldp, q, ldq, idx, B, N, k, C, scale, shift, act, slope, o
 
 
 def edgeconv_dg(p, ldp, q, ldq, idx, B, N, k, C1, C2, s1, t1, w2, s2, t2, act, slope, x1, ld1, x2, ld2):
-    """Two fused edge layers (see lpd_edgeconv_dg); second layer on the tensor cores in "tf32" precision mode."""
+    """Two fused edge layers (see lpd_edgeconv_dg); second layer on the tensor cores in "tf32" precision mode.
+    s1 = t1 = None: p / q already carry the first layer's folded BatchNorm (tf32 mode, k == 20, C1 == C2 == 128)."""
     lib = _lib.load()
     tf32 = _precision == "tf32" and act != ACT_SIGMOID
     fn, label = (lib.lpd_edgeconv_dg_tf32, "lpd_edgeconv_dg_tf32") if tf32 else (lib.lpd_edgeconv_dg, "lpd_edgeconv_dg")
+    if s1 is None and not (tf32 and k == 20 and C1 == 128 and C2 == 128):
+        raise _lib.LpdError("edgeconv_dg: the pre-scaled form (s1 = t1 = None) exists for tf32 mode, k == 20, 128 channels only")
     _call(f"{label}[{C1}x{C2}]", 1, fn, p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), B, N, k, C1, C2,
-          s1.data_ptr(), t1.data_ptr(), w2.data_ptr(), s2.data_ptr(), t2.data_ptr(),
+          _p(s1), _p(t1), w2.data_ptr(), s2.data_ptr(), t2.data_ptr(),
           act, float(slope), _p(x1), ld1, x2.data_ptr(), ld2, _stream())
     return x1, x2
 

@@ -233,6 +233,11 @@ class LPDNet(_LPDBase):
         p["sdg1"], p["tdg1"] = fold_bn(self.convDG1[1])
         p["sdg2"], p["tdg2"] = fold_bn(self.convDG2[1])
         p["ssn1"], p["tsn1"] = fold_bn(self.convSN1[1])
+        # epilogue vectors of the projection GEMMs for the pre-scaled edge kernels: [s | s] and [0 | t]
+        p["spq1"] = torch.cat((p["sdg1"], p["sdg1"])).contiguous()
+        p["tpq1"] = torch.cat((torch.zeros_like(p["tdg1"]), p["tdg1"])).contiguous()
+        p["spq3"] = torch.cat((p["ssn1"], p["ssn1"])).contiguous()
+        p["tpq3"] = torch.cat((torch.zeros_like(p["tsn1"]), p["tsn1"])).contiguous()
         return p
 
     def forward_pm(self, x: torch.Tensor, keep_order: bool = False):
@@ -247,16 +252,24 @@ class LPDNet(_LPDBase):
         dev = h.device
         # feature-space graph: DG1 + DG2 fused, x1 | x2 land in columns 0..255 of the 512-wide pyramid buffer
         idx_f = ops.knn(h.view(B, N, 64), k)
-        pq1 = ops.linear(h, p["wpq1"], M=M, N=256, K=64)
         pyr = torch.empty(M, 512, device=dev, dtype=torch.float32)
-        ops.edgeconv_dg(pq1, 256, pq1[:, 128:], 256, idx_f, B, N, k, 128, 128, p["sdg1"], p["tdg1"], p["wdg2"],
-                        p["sdg2"], p["tdg2"], act, slope, pyr, 512, pyr[:, 128:], 512)
+        if ops.get_precision() == "tf32" and k == 20 and M >= 128:
+            # the reference's own shape: DG1's folded BatchNorm goes into the projection GEMM's epilogue
+            # (P' = s1 * Wn h, Q' = s1 * Wc h + t1), the edge kernel only adds, activates and feeds the tensor cores
+            pq1 = ops.linear(h, p["wpq1"], M=M, N=256, K=64, scale=p["spq1"], shift=p["tpq1"])
+            ops.edgeconv_dg(pq1, 256, pq1[:, 128:], 256, idx_f, B, N, k, 128, 128, None, None, p["wdg2"],
+                            p["sdg2"], p["tdg2"], act, slope, pyr, 512, pyr[:, 128:], 512)
+        else:
+            pq1 = ops.linear(h, p["wpq1"], M=M, N=256, K=64)
+            ops.edgeconv_dg(pq1, 256, pq1[:, 128:], 256, idx_f, B, N, k, 128, 128, p["sdg1"], p["tdg1"], p["wdg2"],
+                            p["sdg2"], p["tdg2"], act, slope, pyr, 512, pyr[:, 128:], 512)
         del pq1
         # Cartesian graph on the untransformed input coordinates: SN1 over x2
         idx_x = ops.knn(xyz_init, k)
-        pq3 = ops.linear(pyr[:, 128:], p["wpq3"], M=M, N=512, K=128, lda=512)
-        ops.edge_gather_ext(pq3, 512, pq3[:, 256:], 512, idx_x, B, N, k, 256, p["ssn1"], p["tsn1"], act, slope,
-                            pyr[:, 256:], 512)
+        # SN1's folded BatchNorm rides in the projection GEMM's epilogue (P' = s Wn x2, Q' = s Wc x2 + t): the gather kernel
+        # then only needs max_m P'_j + Q'_i (no min branch for negative scales, no per-channel constants)
+        pq3 = ops.linear(pyr[:, 128:], p["wpq3"], M=M, N=512, K=128, lda=512, scale=p["spq3"], shift=p["tpq3"])
+        ops.edge_gather_ext(pq3, 512, pq3[:, 256:], 512, idx_x, B, N, k, 256, None, None, act, slope, pyr[:, 256:], 512)
         del pq3
         f = ops.linear(pyr, p["w3"], M=M, N=self.emb_dims, K=512, scale=p["s3"], shift=p["t3"], act=act, slope=slope)
         return f, B, N

@@ -143,6 +143,39 @@ def test_bn_fold_transpose_colmax_splitk(cuda):
     assert np.abs(out - (part.astype(np.float64).sum(0) * g[:20] + b[:20])).max() < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K,lda,out_half", [(300, 64, 1024, 1024, False), (1000, 1024, 512, 512, True), (129, 512, 128, 256, False),
+                                                (4096, 256, 64, 64, True), (128, 68, 72, 80, False)])
+def test_gemm_f16_operands(cuda, M, N, K, lda, out_half):
+    """lpd_gemm_f16: fp16 operands, fp32 accumulation on tcgen05 kind::f16, fused affine + LeakyReLU epilogue, fp32 or fp16
+    output — against float64 on the SAME fp16-rounded operands (so only accumulation order and the output rounding differ)"""
+    r = rng(M + N + K)
+    A = (r.standard_normal((M, lda))).astype(np.float16)
+    W = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float16)
+    sc, sh = r.standard_normal(N).astype(np.float32), r.standard_normal(N).astype(np.float32)
+    ref = A[:, :K].astype(np.float64) @ W.astype(np.float64).T * sc + sh
+    ref = np.where(ref > 0, ref, 0.01 * ref)
+    dA, dW = torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda()
+    got = ops.gemm_f16(dA, dW, M=M, N=N, K=K, lda=lda, out_half=out_half, scale=dev(sc), shift=dev(sh), act=ops.ACT_LEAKY, slope=0.01)
+    assert got.dtype == (torch.float16 if out_half else torch.float32)
+    tol = (2.0 ** -10 if out_half else 1e-5) * max(1.0, np.abs(ref).max())
+    assert np.abs(got.float().cpu().numpy() - ref).max() <= tol
+    # round trip of the conversion kernel
+    x32 = r.standard_normal((37, 50)).astype(np.float32)
+    assert np.array_equal(ops.to_f16(dev(x32)).cpu().numpy(), x32.astype(np.float16))
+
+
+@pytest.mark.parametrize("M,N,K,batch", [(1024, 64, 4096, 3), (128, 64, 64, 1), (200, 72, 1000, 1), (1024, 64, 16384, 2)])
+def test_gemm_f16_tn_contraction_over_rows(cuda, M, N, K, batch):
+    """lpd_gemm_f16_tn: out[z] = A[z]^T . B[z] over the rows of two fp16 point-major maps (the NetVLAD aggregate in f16 mode)"""
+    r = rng(M + N + K + batch)
+    A = r.standard_normal((batch * K, M)).astype(np.float16)
+    Bm = r.random((batch * K, N)).astype(np.float16)
+    got = ops.gemm_f16_tn(torch.from_numpy(A).cuda(), torch.from_numpy(Bm).cuda(), M=M, N=N, K=K, lda=M, ldb=N, batch=batch).cpu().numpy()
+    for z in range(batch):
+        ref = A[z * K:(z + 1) * K].astype(np.float64).T @ Bm[z * K:(z + 1) * K].astype(np.float64)
+        assert np.abs(got[z] - ref).max() <= 2e-6 * K ** 0.5 * max(1.0, np.abs(ref).max()), f"slice {z}"
+
+
 # ------------------------------------------------------------------------------------------------ EdgeConv
 def _leaky(x):
     return np.where(x > 0, x, 0.01 * x)
@@ -166,6 +199,28 @@ def test_edge_gather_ext_vs_materialised_edges(cuda, B, N, k, C):
     ref2 = pb[np.arange(B)[:, None, None], idx].max(2).reshape(B * N, C)
     ops.edge_gather_ext(dev(p), C, None, 0, dev(idx, torch.int32), B, N, k, C, None, None, ops.ACT_NONE, 0.0, out, C)
     assert np.array_equal(out.cpu().numpy(), ref2)
+
+
+@pytest.mark.parametrize("B,N,k,C", [(2, 300, 20, 256), (1, 257, 7, 128), (3, 1000, 32, 256), (1, 129, 1, 128), (2, 64, 21, 256)])
+def test_edge_gather_prescaled_wide_rows(cuda, B, N, k, C):
+    """the pre-scaled form (scale = shift = None, C in {128, 256}: one warp per point, max only): out = act(q + max_m p_j),
+    bit-exact against numpy (an fp32 max and one fp32 add), with a leading dimension wider than C like the model's buffers"""
+    r = rng(N + C + k)
+    ld = 2 * C
+    pq = r.standard_normal((B * N, ld)).astype(np.float32)
+    idx = r.integers(0, N, (B, N, k)).astype(np.int32)
+    P, Q = pq[:, :C].reshape(B, N, C), pq[:, C:]
+    want = _leaky_f32(P[np.arange(B)[:, None, None], idx].max(2).reshape(B * N, C) + Q)
+    d_pq = dev(pq)
+    out = torch.full((B * N, ld), -7.0, device="cuda")
+    ops.edge_gather_ext(d_pq, ld, d_pq[:, C:], ld, dev(idx, torch.int32), B, N, k, C, None, None, ops.ACT_LEAKY, 0.01, out[:, C:], ld)
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, C:], want) and (got[:, :C] == -7.0).all()
+
+
+def _leaky_f32(x):
+    x = x.astype(np.float32)
+    return np.where(x > 0, x, x * np.float32(0.01)).astype(np.float32)
 
 
 @pytest.mark.parametrize("B,N,k,C", [(2, 300, 20, 128), (1, 257, 32, 128), (1, 100, 7, 128), (2, 200, 20, 64), (1, 90, 25, 64)])
@@ -366,6 +421,45 @@ def test_edgeconv_dg_tensor_core_path(cuda, B, N, k, C):
     assert np.abs(got[:, :C] - x1_ref).max() < 1e-5
     scale2 = np.abs(y2).max()
     assert np.abs(got[:, C:] - x2_ref).max() < 2.0 ** -8 * scale2
+
+
+@pytest.mark.parametrize("B,N", [(2, 300), (1, 4096), (3, 1001), (1, 23), (1, 20)])
+def test_edgeconv_dg_prescaled_k20_kernel(cuda, B, N):
+    """the specialised k = 20 / 128-channel kernel (edge_tc20.cu: 24-row point slots, two producer warps per point, first-layer
+    BatchNorm pre-applied to p and q): x1 exact up to one fp32 add, x2 within 2^-8 of the layer-2 scale (TF32 second layer);
+    point counts that do not fill the last 5-point tile, clouds smaller than a tile"""
+    k, C = 20, 128
+    r = rng(N + 77)
+    pq = r.standard_normal((B * N, 2 * C)).astype(np.float32)
+    idx = r.integers(0, N, (B, N, k)).astype(np.int32)
+    s2, t2 = (r.standard_normal(C).astype(np.float32) for _ in range(2))
+    w2 = (r.standard_normal((C, C)) / np.sqrt(C)).astype(np.float32)
+    P, Q = pq[:, :C].reshape(B, N, C), pq[:, C:].reshape(B, N, C)
+    y1 = _leaky((P[np.arange(B)[:, None, None], idx] + Q[:, :, None, :]).astype(np.float64))
+    y2 = _leaky((y1 @ w2.astype(np.float64).T) * s2 + t2)
+    x1_ref, x2_ref = y1.max(2).reshape(B * N, C), y2.max(2).reshape(B * N, C)
+    d_pq = dev(pq)
+    x = torch.zeros(B * N, 4 * C, device="cuda")
+    prev = ops.set_precision("tf32")
+    try:
+        ops.profile(True)
+        ops.edgeconv_dg(d_pq, 2 * C, d_pq[:, C:], 2 * C, dev(idx, torch.int32), B, N, k, C, C, None, None, dev(w2), dev(s2), dev(t2),
+                        ops.ACT_LEAKY, 0.01, x, 4 * C, x[:, C:], 4 * C)
+        labels = [l for l, _, _ in ops.profile(False)]
+    finally:
+        ops.set_precision(prev)
+    assert labels == ["lpd_edgeconv_dg_tf32[128x128]"]
+    got = x.cpu().numpy()
+    assert np.abs(got[:, :C] - x1_ref).max() < 1e-6
+    assert np.abs(got[:, C:2 * C] - x2_ref).max() < 2.0 ** -8 * np.abs(y2).max()
+    assert (got[:, 2 * C:] == 0).all()
+    with pytest.raises(Exception):      # the pre-scaled form exists for k == 20 only
+        ops.set_precision("tf32")
+        try:
+            ops.edgeconv_dg(d_pq, 2 * C, d_pq[:, C:], 2 * C, dev(idx[:, :, :7].copy(), torch.int32), B, N, 7, C, C, None, None, dev(w2), dev(s2),
+                            dev(t2), ops.ACT_LEAKY, 0.01, x, 4 * C, x[:, C:], 4 * C)
+        finally:
+            ops.set_precision(prev)
 
 
 # ------------------------------------------------------------------------------------------------ tensor-core kNN (exact)
