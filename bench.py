@@ -98,6 +98,11 @@ def kernel_work(label: str, B: int, N: int = NPTS, k: int = KNN):
     if label.startswith("lpd_gemm["):
         M, Nn, K, batch = (int(v) for v in label[9:-1].split("x"))
         return 2.0 * M * Nn * K * batch, 4.0 * batch * (M * K + Nn * K + M * Nn)
+    if label.startswith(("lpd_gemm_f16[", "lpd_gemm_f16_tn[")):
+        dims = [int(v) for v in label[label.index("[") + 1:-1].split("x")]
+        M, Nn, K = dims[:3]
+        batch = dims[3] if len(dims) > 3 else 1
+        return 2.0 * M * Nn * K * batch, 2.0 * batch * (M * K + Nn * K) + 4.0 * batch * M * Nn     # fp16 operands
     if label.startswith("lpd_gemm_tf32[") or label.startswith("lpd_gemm_tf32_tn["):
         dims = [int(v) for v in label[label.index("[") + 1:-1].split("x")]
         M, Nn, K = dims[:3]
@@ -107,6 +112,8 @@ def kernel_work(label: str, B: int, N: int = NPTS, k: int = KNN):
         return 2.0 * N * N * 64 * B, 4.0 * B * N * (64 + k)
     if label.startswith("lpd_knn[C=3") or label.startswith("lpd_knn_xyz"):
         return 2.0 * N * N * 3 * B, 4.0 * B * N * (3 + k)
+    if label.startswith("lpd_edgeconv_dg_f16[128"):
+        return 2.0 * N * k * 128 * 128 * B, 2.0 * B * N * (256 + 256) + 4.0 * B * N * k
     if label.startswith("lpd_edgeconv_dg[128") or label.startswith("lpd_edgeconv_dg_tf32[128"):
         return 2.0 * N * k * 128 * 128 * B, 4.0 * B * N * (256 + 256 + k)
     if label.startswith("lpd_edge_gather_ext"):
@@ -485,7 +492,7 @@ FAMILIES = {   # kernel-label prefix -> family of the step (SURVEY §8d stages)
     "EdgeConv DG1+DG2": ("lpd_edgeconv_dg",),
     "EdgeConv SN1 gather": ("lpd_edge_gather_ext",),
     "NetVLAD (assign, aggregate, norms, hidden, gating)": ("lpd_netvlad", "lpd_softmax64", "lpd_splitk_reduce", "lpd_gemm_tf32_tn[1024x64",
-                                                           "lpd_gemm[", "lpd_conv3_vlad", "lpd_hidden"),
+                                                           "lpd_gemm_f16_tn[1024x64", "lpd_gemm[", "lpd_conv3_vlad", "lpd_hidden"),
 }
 
 
@@ -561,12 +568,14 @@ def bench_embed(ctx, tag: str):
                        "frac_of_bf16_sustained": named_flops / (named_ms * 1e-3) / 1e12 / ctx.peaks["bf16_tflops_sustained"]}
         res = {"metric": METRIC if tag == "c2" else C5_METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": ctx.steps,
                "warmup": ctx.warmup, "ms_per_step": t_ms / ctx.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+               "dtype": {"f16": "f16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
                "config": {"workload": ("C2: LPD-Net eval embedding (featnet=lpdnet, kNN k=20 graph features + NetVLAD K=64 D=1024 -> 256), 64 x 4096-pt submaps per GPU per step"
                                        if tag == "c2" else
                                        "C5: LPD-Net eval embedding, stress shape: 32 clouds x 16384 pts per GPU per step (one GPU's share of the 256-cloud batch at 8 GPUs), k=32"),
-                          "precision": ("tf32 tensor-core GEMMs (fp32 storage, fp32 accumulate; kNN and its input layers exact fp32)"
-                                        if args.precision == "tf32" else "strict fp32"),
+                          "precision": {"f16": "fp16 activations and operands downstream of the kNN (round to nearest), tcgen05 kind::f16, fp32 accumulate; "
+                                               "kNN and its input layers exact fp32",
+                                        "tf32": "tf32 tensor-core GEMMs (fp32 storage, fp32 accumulate; kNN and its input layers exact fp32)",
+                                        "fp32": "strict fp32"}[args.precision],
                           "submaps_per_gpu_per_step": B, "points": N, "k": k, "sharding": f"batch-sharded dp{ctx.world}, no collective",
                           "launch": "each timed step = D2D copy of the step's input + ONE CUDA-graph replay of the eager kernel sequence",
                           "l2": "256 MiB memset between timed steps (untimed); 4 rotating input batches; intermediates > 1 GiB/step"},
@@ -935,9 +944,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
-                    help="tf32: dense layers on tcgen05 tensor cores (descriptor error vs the reference measured and reported in config); "
-                         "fp32: strict mode")
+    ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"],
+                    help="f16: fp16 activations / operands downstream of the kNN on tcgen05 kind::f16, fp32 accumulation (eval path); "
+                         "tf32: dense layers on tcgen05 kind::tf32; fp32: strict mode.  The descriptor error vs the reference is measured "
+                         "and reported in config.")
     ap.add_argument("--workload", default="all", choices=["all", "c2", "c3", "c4", "c5"],
                     help="all (default): C2 as the top-level line (the configuration BASELINE.json's metric is quoted on) with C3, C4, C5 "
                          "under `workloads`; or one workload as the top-level line")

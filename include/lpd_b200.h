@@ -182,6 +182,21 @@ int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void* C, int ld
 int lpd_gemm_f16_tn(const void* A, int lda, const void* B, int ldb, float* C, int ldc, long long strideC,
                     int M, int N, int K, int batch, void* stream);
 int lpd_f32_to_f16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols, void* stream);
+/* lpd_gemm_tf32 with the result written as fp16 (C [M][ldc] halves): the projection in front of the f16-mode edge kernels, whose
+ * input (the conv2 feature map that also feeds the exact feature-space kNN) stays fp32. */
+int lpd_gemm_tf32_out16(const float* A, int lda, const float* B, int ldb, void* C, int ldc, int M, int N, int K,
+                        const float* scale, const float* shift, int act, float slope, void* stream);
+/* lpd_softmax64 that also writes the probabilities as fp16 (a_h [M][64]): the B operand of the f16-mode NetVLAD aggregate. */
+int lpd_softmax64_f16(float* a, long long M, void* a_h, void* stream);
+/* f16-mode forms of the pre-scaled edge kernels (fp16 rows in and out, see lpd_edge_gather_ext / lpd_edgeconv_dg_tf32):
+ *   lpd_edge_gather_max_f16:  out[i][:] = act(q[i][:] + max_m p[j(i,m)][:]),  C == 256            (csrc/edge.cu)
+ *   lpd_edgeconv_dg20_f16:    k == 20, 128 channels; y1 = act(p_j + q_i) and W2 in fp16, second layer on tcgen05 kind::f16,
+ *                             x1 / x2 written as fp16                                             (csrc/edge_tc20.cu) */
+int lpd_edge_gather_max_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N, int k, int C,
+                            int act, float slope, void* out, int ldo, void* stream);
+int lpd_edgeconv_dg20_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N,
+                          const void* w2, const float* s2, const float* t2, int act, float slope,
+                          void* x1, int ld1, void* x2, int ld2, void* stream);
 
 /* Fused input layers of the LPD-Net feature nets (lpdnet_model.py:231-232, :86-87), strict fp32, one pass:
  *     out[m][:] = act(s2 * (W2 . act(s1 * (W1 . x[m][0..D)) + t1)) + t2),   W1 [64][D], W2 [64][64], D <= 8

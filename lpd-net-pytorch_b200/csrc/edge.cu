@@ -9,6 +9,7 @@
 //     multiplies them by the second-layer weight (kept resident in shared memory by a persistent
 //     CTA) and max-reduces over the k neighbours in registers.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace lpd {
 
@@ -196,6 +197,57 @@ edge_gather_max_kernel(const float* __restrict__ p, int ldp, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same with FP16 rows ("f16" precision mode): p, q, out are fp16 matrices with 256 channels (512 bytes per row: ONE LDG.128
+// per lane and row — half the bytes of the fp32 form through the L1 / L2 data path, which is what bounds this kernel).  The max
+// over the neighbours is taken on the fp16 values directly (exact), the centre term and the activation in fp32, one rounding
+// to nearest on the way out.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+edge_gather_max_h_kernel(const __half* __restrict__ p, int ldp, const __half* __restrict__ q, int ldq,
+                         const int* __restrict__ idx, long long total_pts, int N, int k, int act, float slope,
+                         __half* __restrict__ out, int ldo) {
+    const int lane = threadIdx.x & 31;
+    const long long pt = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pt >= total_pts) return;
+    const int myj = lane < k ? __ldg(idx + pt * k + lane) : 0;
+    const __half* base = p + (pt / N) * N * ldp + lane * 8;
+    const uint4 qraw = q ? __ldg(reinterpret_cast<const uint4*>(q + pt * ldq + lane * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+    __half2 mx[4] = {ninf, ninf, ninf, ninf};
+    int m = 0;
+    for (; m + 5 <= k; m += 5) {                     // 5 rows in flight per lane
+        uint4 r[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int j = __shfl_sync(0xffffffffu, myj, m + u);
+            r[u] = __ldg(reinterpret_cast<const uint4*>(base + (unsigned)(j * ldp)));
+        }
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const __half2* h = reinterpret_cast<const __half2*>(&r[u]);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) mx[v] = __hmax2(mx[v], h[v]);
+        }
+    }
+    for (; m < k; ++m) {
+        const int j = __shfl_sync(0xffffffffu, myj, m);
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(base + (unsigned)(j * ldp)));
+        const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) mx[v] = __hmax2(mx[v], h[v]);
+    }
+    const __half2* qh = reinterpret_cast<const __half2*>(&qraw);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const float2 a = __half22float2(mx[v]), b = __half22float2(qh[v]);
+        oh[v] = __floats2half2_rn(act2(a.x + b.x, act, slope), act2(a.y + b.y, act, slope));
+    }
+    *reinterpret_cast<uint4*>(out + pt * ldo + lane * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Two chained edge layers, one warp per point, persistent CTAs with W2 resident in shared memory.
 // ------------------------------------------------------------------------------------------------
 struct DgParams {
@@ -355,6 +407,25 @@ extern "C" int lpd_edge_gather_ext(const float* p, int ldp, const float* q, int 
     LPD_REQUIRE(blocks <= 0x7fffffffLL);
     edge_gather_ext_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p, ldp, q, ldq, idx, total, N, k, C, scale, shift,
                                                                          act, slope, out, ldo);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+extern "C" int lpd_edge_gather_max_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N, int k, int C,
+                                       int act, float slope, void* out, int ldo, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(p && idx && out && B >= 1 && N >= 1 && k >= 1 && k <= 32 && k <= N);
+    LPD_REQUIRE(C == 256);
+    LPD_REQUIRE(ldp % 8 == 0 && ldo % 8 == 0 && ldp >= C && ldo >= C && (!q || (ldq % 8 == 0 && ldq >= C)));
+    LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || act == LPD_ACT_LEAKY);
+    LPD_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)q & 15) == 0);
+    LPD_REQUIRE((long long)N * ldp < (1ll << 31));
+    const long long total = (long long)B * N;
+    const long long blocks = (total + 7) / 8;
+    LPD_REQUIRE(blocks <= 0x7fffffffLL);
+    edge_gather_max_h_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __half*>(p), ldp, reinterpret_cast<const __half*>(q), ldq, idx, total, N, k, act, slope,
+        reinterpret_cast<__half*>(out), ldo);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }

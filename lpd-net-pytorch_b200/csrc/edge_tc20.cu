@@ -12,6 +12,7 @@
 //   * TWO producer warps per point, each owning one half of the channels (16 lanes x float4 per row, two rows per warp
 //     iteration): 20 producer warps in two groups of 10 (one group per shared-memory / TMEM stage) + 4 epilogue warps.
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace lpd {
 namespace tc {
@@ -229,6 +230,227 @@ edgeconv_dg20_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20Params 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// FP16 form ("f16" precision mode): p' / q' rows, W2, the activated edge rows and both outputs are fp16; the second edge layer
+// runs on tcgen05 kind::f16 (fp32 accumulation).  A gathered row is 256 bytes instead of 512, an operand tile 32 KB instead of
+// 64, and the first layer is three half2 instructions per two values (add, multiply by the slope, max).  Same roles: 4 epilogue
+// warps + 2 groups of 10 producer warps (two per point, one 64-channel k-block each, FOUR rows per warp iteration).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t D20H_KB_BYTES = 128 * 128;          // one 64-channel k-block of a 128-row fp16 operand tile
+constexpr uint32_t D20H_OP_BYTES = 2 * D20H_KB_BYTES;  // 32 KB
+
+struct Dg20hParams {
+    const __half* p; const __half* q; const int* idx;
+    const float* s2; const float* t2;
+    __half* x1; __half* x2;
+    int ldp, ldq, ld1, ld2;
+    long long total_pts; int N;
+    float neg_slope;
+    long long num_tiles;
+};
+
+__global__ void __launch_bounds__(D20_THREADS, 1)
+edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* w_s = smem;
+    uint8_t* y_s = smem + D20H_OP_BYTES;              // [2][OP_BYTES]
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + 3 * D20H_OP_BYTES);
+    uint64_t* yfull = wfull + 1;
+    uint64_t* yempty = yfull + 2;
+    uint64_t* tfull = yempty + 2;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (uint32_t i = threadIdx.x; i < 2 * D20H_OP_BYTES / 16; i += D20_THREADS)
+        reinterpret_cast<uint4*>(y_s)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == D20_ALLOC_WARP) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w2)) : "memory");
+            mbar_init(wfull, 1);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&yfull[s], D20_GROUP_WARPS);
+                mbar_init(&yempty[s], 1);
+                mbar_init(&tfull[s], 1);
+                mbar_init(&tempty[s], D20_EPI_WARPS);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= D20_EPI_WARPS) {
+        const int pwarp = warp - D20_EPI_WARPS;
+        const int grp = pwarp / D20_GROUP_WARPS, gw = pwarp % D20_GROUP_WARPS;
+        const int pl = gw >> 1, chalf = gw & 1;                    // point slot, 64-channel k-block
+        const bool issuer = gw == 0;
+        if (warp == D20_ALLOC_WARP && lane == 0) {
+            mbar_expect_tx(wfull, D20H_OP_BYTES);
+            for (int kb2 = 0; kb2 < 2; ++kb2) tma_load_2d(w_s + kb2 * D20H_KB_BYTES, &tmap_w2, wfull, kb2 * 64, 0);
+        }
+        // kind::f16, fp16 operands, fp32 accumulate, M = N = 128
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t w_addr = smem_u32(w_s);
+        bool w_ready = false;
+        const int sr = lane >> 3, l8 = lane & 7;                   // row of the quadruple, 16-byte chunk (8 channels) inside the k-block
+        const int ch = chalf * 64 + l8 * 8;
+        // store address of edge row m = 4 i + sr:  slot base + m * 128 + ((l8 ^ (m & 7)) << 4),  (m & 7) = 4 (i & 1) + sr
+        const uint32_t xo0 = (uint32_t)((l8 ^ sr) << 4), xo1 = (uint32_t)((l8 ^ sr ^ 4) << 4);
+        uint8_t* ybase = y_s + grp * D20H_OP_BYTES + chalf * D20H_KB_BYTES + (pl * D20_SLOT + sr) * 128;
+        const long long tstep = 2LL * gridDim.x;
+        long long t = blockIdx.x + (long long)grp * gridDim.x;
+        int nj = 0;
+        uint4 nq = make_uint4(0u, 0u, 0u, 0u);
+        auto prefetch = [&](long long tile) {
+            const long long pt = tile * D20_PTS + pl;
+            if (tile < P.num_tiles && pt < P.total_pts) {
+                nj = (lane < D20_K) ? __ldg(P.idx + pt * D20_K + lane) : 0;
+                nq = __ldg(reinterpret_cast<const uint4*>(P.q + pt * P.ldq + ch));
+            }
+        };
+        prefetch(t);
+        const __half2 slope2 = __float2half2_rn(P.neg_slope);
+        const __half2 ninf = __float2half2_rn(-INFINITY);
+        for (uint32_t it = 0; t < P.num_tiles; t += tstep, ++it) {
+            const uint32_t ph = it & 1;
+            const int myj = nj;
+            const uint4 qraw = nq;
+            const long long pt = t * D20_PTS + pl;
+            prefetch(t + tstep);
+            mbar_wait(&yempty[grp], ph ^ 1);
+            if (pt < P.total_pts) {
+                const __half* pbase = P.p + (pt / P.N) * P.N * P.ldp + ch;
+                const __half2* qh = reinterpret_cast<const __half2*>(&qraw);
+                __half2 best[4] = {ninf, ninf, ninf, ninf};
+                uint4 pv[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {                                   // all 20 rows of the point in flight: 5 per lane
+                    const int j = __shfl_sync(kFull, myj, 4 * i + sr);
+                    pv[i] = __ldg(reinterpret_cast<const uint4*>(pbase + (unsigned)(j * P.ldp)));
+                }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const __half2* ph2 = reinterpret_cast<const __half2*>(&pv[i]);
+                    uint4 y;
+                    __half2* yh = reinterpret_cast<__half2*>(&y);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        best[v] = __hmax2(best[v], ph2[v]);
+                        const __half2 z = __hadd2(ph2[v], qh[v]);
+                        yh[v] = __hmax2(z, __hmul2(z, slope2));
+                    }
+                    *reinterpret_cast<uint4*>(ybase + i * 512 + ((i & 1) ? xo1 : xo0)) = y;
+                }
+                if (P.x1) {
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t b = *reinterpret_cast<uint32_t*>(&best[v]);
+                        uint32_t o8 = __shfl_xor_sync(kFull, b, 8);
+                        __half2 m2 = __hmax2(best[v], *reinterpret_cast<__half2*>(&o8));
+                        b = *reinterpret_cast<uint32_t*>(&m2);
+                        uint32_t o16 = __shfl_xor_sync(kFull, b, 16);
+                        m2 = __hmax2(m2, *reinterpret_cast<__half2*>(&o16));
+                        const __half2 z = __hadd2(m2, qh[v]);                   // max_m act(p'_m + q') = act(max_m p'_m + q')
+                        oh[v] = __hmax2(z, __hmul2(z, slope2));
+                    }
+                    if (sr == 0) *reinterpret_cast<uint4*>(P.x1 + pt * P.ld1 + ch) = o;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&yfull[grp]);
+            if (issuer) {
+                if (!w_ready) { mbar_wait(wfull, 0); w_ready = true; }
+                mbar_wait(&tempty[grp], ph ^ 1);
+                mbar_wait(&yfull[grp], ph);
+                tc_fence_after();
+                const uint32_t y_addr = smem_u32(y_s + grp * D20H_OP_BYTES);
+#pragma unroll
+                for (int kb2 = 0; kb2 < 2; ++kb2) {
+                    const uint64_t da = make_smem_desc(w_addr + kb2 * D20H_KB_BYTES), db = make_smem_desc(y_addr + kb2 * D20H_KB_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {             // 16 channels = 32 bytes per MMA
+                        const uint32_t acc = (kb2 | ks) != 0 ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p, q;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "elect.sync _|q, 0xffffffff;\n\t"
+                            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem_base + grp * D20_ACC_STRIDE), "l"(da + (uint64_t)(ks * 2)), "l"(db + (uint64_t)(ks * 2)), "r"(idesc), "r"(acc)
+                            : "memory");
+                    }
+                }
+                tc_commit_e(&yempty[grp]);
+                tc_commit_e(&tfull[grp]);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int ch = warp * 32 + lane;
+        const float s2 = __ldg(P.s2 + ch), t2 = __ldg(P.t2 + ch);
+        long long t = blockIdx.x;
+        for (uint32_t it = 0; t < P.num_tiles; t += gridDim.x, ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            mbar_wait(&tfull[s], ph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int pl = 0; pl < D20_PTS; ++pl) {
+                const long long pt = t * D20_PTS + pl;
+                if (pt >= P.total_pts) break;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + s * D20_ACC_STRIDE + pl * D20_SLOT;
+                uint32_t r[20];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(taddr + 16));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float a4[4], b4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { a4[u] = __uint_as_float(r[u]); b4[u] = a4[u]; }
+#pragma unroll
+                for (int j = 4; j < 20; j += 2) {
+                    const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+                    a4[(j >> 1) & 3] = fmaxf(fmaxf(a4[(j >> 1) & 3], v0), v1);
+                    b4[(j >> 1) & 3] = fminf(fminf(b4[(j >> 1) & 3], v0), v1);
+                }
+                const float mx = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));
+                const float mn = fminf(fminf(b4[0], b4[1]), fminf(b4[2], b4[3]));
+                float v = fmaf(s2, s2 >= 0.f ? mx : mn, t2);
+                v = fmaxf(v, v * P.neg_slope);
+                // two channels per store: even lanes write their own and their right neighbour's value as one half2
+                const float vn = __shfl_down_sync(kFull, v, 1);
+                if ((lane & 1) == 0) {
+                    __half2 h;
+                    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(*reinterpret_cast<uint32_t*>(&h)) : "f"(vn), "f"(v));
+                    *reinterpret_cast<__half2*>(P.x2 + pt * P.ld2 + ch) = h;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[s]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == D20_ALLOC_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // called by lpd_edgeconv_dg_tf32 (edge_tc.cu) for k == 20, C1 == C2 == 128, s1 == t1 == NULL
 int dg20_tc_run(const float* p, int ldp, const float* q, int ldq, const int32_t* idx, int B, int N, const float* w2,
                 const float* s2, const float* t2, float neg_slope, float* x1, int ld1, float* x2, int ld2, cudaStream_t st) {
@@ -253,3 +475,45 @@ int dg20_tc_run(const float* p, int ldp, const float* q, int ldq, const int32_t*
 
 }  // namespace tc
 }  // namespace lpd
+
+extern "C" int lpd_edgeconv_dg20_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N,
+                                     const void* w2, const float* s2, const float* t2, int act, float slope,
+                                     void* x1, int ld1, void* x2, int ld2, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(p && q && idx && w2 && s2 && t2 && x2 && B >= 1 && N >= 20);
+    LPD_REQUIRE(ldp % 8 == 0 && ldq % 8 == 0 && ld2 % 2 == 0 && (!x1 || ld1 % 8 == 0));
+    LPD_REQUIRE(ldp >= 128 && ldq >= 128 && ld2 >= 128 && (!x1 || ld1 >= 128));
+    LPD_REQUIRE((long long)N * ldp < (1ll << 31));
+    LPD_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)q & 15) == 0 && ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)x2 & 3) == 0 && ((uintptr_t)w2 & 15) == 0);
+    LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || (act == LPD_ACT_LEAKY && slope >= 0.f && slope <= 1.f));
+    int dev = 0, major = 0, sms = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (major != 10) return LPD_EUNSUPPORTED;
+    tc::Dg20hParams P;
+    P.p = reinterpret_cast<const __half*>(p); P.q = reinterpret_cast<const __half*>(q); P.idx = idx; P.s2 = s2; P.t2 = t2;
+    P.x1 = reinterpret_cast<__half*>(x1); P.x2 = reinterpret_cast<__half*>(x2);
+    P.ldp = ldp; P.ldq = ldq; P.ld1 = ld1; P.ld2 = ld2; P.total_pts = (long long)B * N; P.N = N;
+    P.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
+    P.num_tiles = (P.total_pts + tc::D20_PTS - 1) / tc::D20_PTS;
+    // W2 fp16 [128][128]: boxes of 64 halves x 128 rows, 128B swizzle
+    tc::EncodeTiledFn enc = tc::get_encode();
+    if (!enc) return LPD_ECUDA;
+    CUtensorMap tw;
+    cuuint64_t dims[2] = {128u, 128u};
+    cuuint64_t strides[1] = {256u};
+    cuuint32_t box[2] = {64u, 128u};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled (fp16 W2) failed");
+        return LPD_ECUDA;
+    }
+    constexpr size_t smem = 3 * (size_t)tc::D20H_OP_BYTES + 256;
+    LPD_CUDA_CHECK(allow_smem(tc::edgeconv_dg20_h_kernel, smem));
+    const int grid = (int)(P.num_tiles < sms ? P.num_tiles : sms);
+    tc::edgeconv_dg20_h_kernel<<<grid, tc::D20_THREADS, smem, as_stream(stream)>>>(tw, P);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}

@@ -408,6 +408,34 @@ extern "C" int lpd_gemm_tf32_ex(const float* A, int lda, const float* B, int ldb
     return tc::launch<256, 4>(ta, tb, p, st);
 }
 
+extern "C" int lpd_gemm_tf32_out16(const float* A, int lda, const float* B, int ldb, void* C, int ldc, int M, int N, int K,
+                                   const float* scale, const float* shift, int act, float slope, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1);
+    LPD_REQUIRE(lda >= K && ldb >= K && ldc >= N);
+    LPD_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0 && (N % 4) == 0);
+    LPD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 7) == 0);
+    LPD_REQUIRE(act == LPD_ACT_NONE || act == LPD_ACT_RELU || (act == LPD_ACT_LEAKY && slope >= 0.f && slope <= 1.f));
+    int dev = 0, major = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return LPD_EUNSUPPORTED;
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    CUtensorMap ta, tb;
+    int rc = tc::make_tmap(&ta, A, M, K, lda, tc::BM);
+    if (rc != LPD_OK) return rc;
+    rc = tc::make_tmap(&tb, B, N, K, ldb, BN);
+    if (rc != LPD_OK) return rc;
+    tc::Params p;
+    p.C = reinterpret_cast<float*>(C); p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = scale; p.shift = shift;
+    p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
+    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0;
+    cudaStream_t st = as_stream(stream);
+    if (BN == 64) return tc::launch<64, 8, false, float, true>(ta, tb, p, st);
+    if (BN == 128) return tc::launch<128, 6, false, float, true>(ta, tb, p, st);
+    return tc::launch<256, 4, false, float, true>(ta, tb, p, st);
+}
+
 extern "C" int lpd_gemm_tf32(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                              int M, int N, int K, const float* scale, const float* shift, int act, float slope,
                              void* stream) {

@@ -3,11 +3,12 @@
 //   the a_sum * cluster_weights2 residual, intra-normalisation over D, global L2 normalisation.
 // The contractions themselves (X.Wc, A^T.X, v.W_h, h.W_g) go through lpd_gemm.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace lpd {
 
 // in place: a[m][0..63] = softmax(a[m][0..63]); one warp per row, 2 values per lane
-__global__ void __launch_bounds__(256) softmax64_kernel(float* __restrict__ a, long long M) {
+__global__ void __launch_bounds__(256) softmax64_kernel(float* __restrict__ a, long long M, __half2* __restrict__ a_h = nullptr) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(256) softmax64_kernel(float* __restrict__ a, l
     v.x = v.x / s;
     v.y = v.y / s;
     *reinterpret_cast<float2*>(a + row * 64 + lane * 2) = v;
+    if (a_h) a_h[row * 32 + lane] = __floats2half2_rn(v.x, v.y);       // fp16 copy: the B operand of the f16-mode aggregate
 }
 
 constexpr int ASUM_SPLITS = 8;
@@ -110,6 +112,14 @@ extern "C" int lpd_softmax64(float* a, long long M, void* stream) {
     using namespace lpd;
     LPD_REQUIRE(a && M >= 1);
     softmax64_kernel<<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(a, M);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+extern "C" int lpd_softmax64_f16(float* a, long long M, void* a_h, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(a && a_h && M >= 1 && ((uintptr_t)a_h & 3) == 0);
+    softmax64_kernel<<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(a, M, reinterpret_cast<__half2*>(a_h));
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }

@@ -25,7 +25,7 @@ A_MK, A_KM, B_NK, B_KN = ops.A_MK, ops.A_KM, ops.B_NK, ops.B_KN
 def dgrad(dz, lddz, w, rows, N, K, out=None, ldc=None, accumulate=False, tf32_ok=True):
     """da[r][k] (+)= sum_n dz[r][n] * w[n][k]   (input gradient of z = a . w^T, w [N, K]).
     In "tf32" precision mode the product runs on the tensor cores against a transposed copy of the (small) weight."""
-    if (tf32_ok and ops.get_precision() == "tf32" and N >= 32 and N % 4 == 0 and lddz % 4 == 0 and K >= 64
+    if (tf32_ok and ops.get_precision() != "fp32" and N >= 32 and N % 4 == 0 and lddz % 4 == 0 and K >= 64
             and K % 4 == 0 and rows >= 128 and (ldc is None or ldc % 4 == 0) and dz.data_ptr() % 16 == 0
             and (out is None or out.data_ptr() % 16 == 0)):
         wt = ops.transpose(w.unsqueeze(0))[0]                                   # [K, N]
@@ -542,7 +542,7 @@ class NetVLADTrain:
         self.f, self.B, self.M = f, B, M
         wc = nv.cluster_weights.detach()
         # soft assignment: a = softmax(BN(f . Wc))                                            :48-59
-        if ops.get_precision() == "tf32" and M >= 128 and D % 4 == 0:
+        if ops.get_precision() != "fp32" and M >= 128 and D % 4 == 0:
             self.apre = ops.gemm_tf32(f, ops.transpose(wc.unsqueeze(0))[0], M=M, N=K, K=D)
         else:
             self.apre = ops.gemm(f, wc, a_layout=A_MK, b_layout=B_KN, M=M, N=K, K=D, lda=D, ldb=K)
@@ -605,7 +605,7 @@ class NetVLADTrain:
         grads.add(nv.cluster_weights2, dwc2)
         f, a = self.f, self.a
         # vraw[b] = f[b]^T a[b]:  da[b] = f[b] . dvraw[b] ;  df[b] = a[b] . dvraw[b]^T (accumulated below)
-        tc_ok = ops.get_precision() == "tf32" and N >= 128 and D % 4 == 0
+        tc_ok = ops.get_precision() != "fp32" and N >= 128 and D % 4 == 0
         if tc_ok:
             dvraw_t = ops.transpose(dvraw.view(B, D, K))                            # [B, K, D]: K-contiguous weight slices
             da = ops.gemm_tf32(f, dvraw_t, M=N, N=K, K=D, lda=D, batch=B,
@@ -620,7 +620,7 @@ class NetVLADTrain:
         grads.add(nv.cluster_weights, ops.wgrad(f, D, dapre, K, M, D, K))           # dWc[d][k] = sum_m f[m][d] dapre[m][k]
         # df = dapre . Wc^T  (z = f . Wc  <=>  weight [N=K][K=D] = Wc^T, i.e. "w" of dgrad is Wc^T [K, D])
         df = torch.empty(M, D, device=f.device, dtype=torch.float32)
-        if ops.get_precision() == "tf32" and M >= 128:
+        if ops.get_precision() != "fp32" and M >= 128:
             ops.gemm_tf32(dapre, wc, M=M, N=D, K=K, lda=K, out=df, ldc=D)           # Wc [D][K] is already K-contiguous
         else:
             ops.gemm(dapre, wc, a_layout=A_MK, b_layout=B_NK, M=M, N=D, K=K, lda=K, ldb=K, out=df, ldc=D)

@@ -88,6 +88,8 @@ class NetVLADLoupe(nn.Module):
         p = {"wc": self.cluster_weights.detach().contiguous(), "wc2": self.cluster_weights2.detach()[0].contiguous(),
              "wh": self.hidden1_weights.detach().contiguous()}
         p["wct"] = ops.transpose(p["wc"].unsqueeze(0))[0]      # [K, D]: K-contiguous operand for the tensor-core path
+        if p["wct"].is_cuda:
+            p["wct_h"] = ops.to_f16(p["wct"])                  # "f16" precision mode
         if self.add_batch_norm:
             p["s1"], p["t1"] = fold_bn(self.bn1)
         else:
@@ -103,11 +105,16 @@ class NetVLADLoupe(nn.Module):
         p = self._prep.get(self, self._build)
         N, D, K, O = self.max_samples, self.feature_size, self.cluster_size, self.output_dim
         M = B * N
-        if ops.get_precision() == "tf32" and M >= 128 and D % 4 == 0:                         # :48-59
+        if f.dtype == torch.float16:                                                          # "f16" mode: F arrives as fp16
+            a, a_h = ops.softmax64_f16(ops.gemm_f16(f, p["wct_h"], M=M, N=K, K=D, scale=p["s1"], shift=p["t1"]), M)   # :48-59
+            vraw = ops.gemm_f16_tn(f, a_h, M=D, N=K, K=N, lda=D, ldb=K, batch=B)              # :64-66 -> [B, D, K]
+        elif ops.get_precision() != "fp32" and M >= 128 and D % 4 == 0:                       # :48-59
             a = ops.softmax64(ops.gemm_tf32(f, p["wct"], M=M, N=K, K=D, scale=p["s1"], shift=p["t1"]), M)
         else:
             a = ops.netvlad_assign(f, M, D, p["wc"], p["s1"], p["t1"], K)
-        if ops._tn_ok(f, a, D, K, N, D, K, B):
+        if f.dtype == torch.float16:
+            pass
+        elif ops._tn_ok(f, a, D, K, N, D, K, B):
             vraw = ops.gemm_tf32_tn(f, a, M=D, N=K, K=N, lda=D, ldb=K, batch=B)               # :64-66 -> [B, D, K]
         else:
             vraw = ops.gemm(f, a, a_layout=ops.A_KM, b_layout=ops.B_KN, M=D, N=K, K=N, lda=D, ldb=K, batch=B,
@@ -313,7 +320,10 @@ class PointNetVlad(nn.Module):
             from ..train import forward_train
             return forward_train(self, x)
         if self.emb_nn is not None:
-            f, B, N = self.emb_nn.forward_pm(x)
+            # "f16" precision mode: fp16 activations downstream of the kNN, for the configuration the kernels are specialised for
+            f16 = (ops.get_precision() == "f16" and isinstance(self.emb_nn, LPDNet) and self.emb_nn.k == 20 and x.size(2) % 64 == 0
+                   and x.size(0) * x.size(2) >= 128 and self.net_vlad.cluster_size == 64 and self.net_vlad.feature_size % 8 == 0)
+            f, B, N = self.emb_nn.forward_pm(x, f16=True) if f16 else self.emb_nn.forward_pm(x)
         else:
             if self.point_net.max_pool:
                 raise ValueError("PointNetVlad needs the per-point feature map: construct with max_pool=False")

@@ -238,11 +238,15 @@ class LPDNet(_LPDBase):
         p["tpq1"] = torch.cat((torch.zeros_like(p["tdg1"]), p["tdg1"])).contiguous()
         p["spq3"] = torch.cat((p["ssn1"], p["ssn1"])).contiguous()
         p["tpq3"] = torch.cat((torch.zeros_like(p["tsn1"]), p["tsn1"])).contiguous()
+        if p["w3"].is_cuda:      # fp16 copies of the weights the "f16" precision mode multiplies with (rounded to nearest, once)
+            p["wdg2_h"], p["wpq3_h"], p["w3_h"] = ops.to_f16(p["wdg2"]), ops.to_f16(p["wpq3"]), ops.to_f16(p["w3"])
         return p
 
-    def forward_pm(self, x: torch.Tensor, keep_order: bool = False):
+    def forward_pm(self, x: torch.Tensor, keep_order: bool = False, f16: bool = False):
         """-> (F [B*N, emb] point-major, B, N).  Unless keep_order, the rows of every cloud are in spatial (grid-cell)
-        order (ops.SPATIAL_ORDER): PointNetVlad feeds them to NetVLAD, which sums over the points."""
+        order (ops.SPATIAL_ORDER): PointNetVlad feeds them to NetVLAD, which sums over the points.
+        f16 (PointNetVlad.forward in "f16" precision mode, k == 20): F and every activation downstream of the feature-space kNN
+        are fp16 tensors; conv1 / conv2 and both kNN graphs stay exact fp32."""
         require_cuda(x, "LPDNet")
         training_unsupported(self, "LPDNet")
         p = self._prep.get(self, self._build)
@@ -250,10 +254,22 @@ class LPDNet(_LPDBase):
         M, k = B * N, self.k
         act, slope = _act_code(self)
         dev = h.device
-        # feature-space graph: DG1 + DG2 fused, x1 | x2 land in columns 0..255 of the 512-wide pyramid buffer
         idx_f = ops.knn(h.view(B, N, 64), k)
+        if f16 and k == 20 and M >= 128 and self.emb_dims % 4 == 0:
+            pq1 = ops.gemm_tf32_out16(h, p["wpq1"], M=M, N=256, K=64, scale=p["spq1"], shift=p["tpq1"])
+            pyr = torch.empty(M, 512, device=dev, dtype=torch.float16)
+            ops.edgeconv_dg20_f16(pq1, 256, pq1[:, 128:], 256, idx_f, B, N, p["wdg2_h"], p["sdg2"], p["tdg2"], act, slope,
+                                  pyr, 512, pyr[:, 128:], 512)
+            del pq1
+            idx_x = ops.knn(xyz_init, k)
+            pq3 = ops.gemm_f16(pyr[:, 128:], p["wpq3_h"], M=M, N=512, K=128, lda=512, out_half=True, scale=p["spq3"], shift=p["tpq3"])
+            ops.edge_gather_max_f16(pq3, 512, pq3[:, 256:], 512, idx_x, B, N, k, 256, act, slope, pyr[:, 256:], 512)
+            del pq3
+            f = ops.gemm_f16(pyr, p["w3_h"], M=M, N=self.emb_dims, K=512, out_half=True, scale=p["s3"], shift=p["t3"], act=act, slope=slope)
+            return f, B, N
+        # feature-space graph: DG1 + DG2 fused, x1 | x2 land in columns 0..255 of the 512-wide pyramid buffer
         pyr = torch.empty(M, 512, device=dev, dtype=torch.float32)
-        if ops.get_precision() == "tf32" and k == 20 and M >= 128:
+        if ops.get_precision() != "fp32" and k == 20 and M >= 128:
             # the reference's own shape: DG1's folded BatchNorm goes into the projection GEMM's epilogue
             # (P' = s1 * Wn h, Q' = s1 * Wc h + t1), the edge kernel only adds, activates and feeds the tensor cores
             pq1 = ops.linear(h, p["wpq1"], M=M, N=256, K=64, scale=p["spq1"], shift=p["tpq1"])

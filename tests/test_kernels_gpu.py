@@ -462,6 +462,49 @@ def test_edgeconv_dg_prescaled_k20_kernel(cuda, B, N):
             ops.set_precision(prev)
 
 
+@pytest.mark.parametrize("B,N,k", [(2, 300, 20), (1, 1000, 32), (3, 64, 7)])
+def test_edge_gather_max_f16(cuda, B, N, k):
+    """fp16 rows, C = 256: out = fp16(act(q + max_m p_j)) — exact against numpy on the same fp16 inputs"""
+    C, ld = 256, 512
+    r = rng(N + k + 5)
+    pq = r.standard_normal((B * N, ld)).astype(np.float16)
+    idx = r.integers(0, N, (B, N, k)).astype(np.int32)
+    P = pq[:, :C].reshape(B, N, C)
+    mx = P[np.arange(B)[:, None, None], idx].max(2).reshape(B * N, C).astype(np.float32)
+    v = mx + pq[:, C:].astype(np.float32)
+    want = np.where(v > 0, v, v * np.float32(0.01)).astype(np.float16)
+    d_pq = torch.from_numpy(pq).cuda()
+    out = torch.zeros(B * N, ld, device="cuda", dtype=torch.float16)
+    ops.edge_gather_max_f16(d_pq, ld, d_pq[:, C:], ld, dev(idx, torch.int32), B, N, k, C, ops.ACT_LEAKY, 0.01, out[:, C:], ld)
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, C:], want) and (got[:, :C] == 0).all()
+
+
+@pytest.mark.parametrize("B,N", [(2, 300), (1, 4096), (3, 1001), (1, 20)])
+def test_edgeconv_dg20_f16_kernel(cuda, B, N):
+    """edge_tc20.cu, fp16 form: y1 = fp16(leaky(p_j + q_i)) in half2 arithmetic, second layer fp16 x fp16 -> fp32 on tcgen05,
+    x1 / x2 written as fp16.  Against float64 on the same fp16 inputs: x1 within one fp16 rounding of the exact value, x2 within
+    2^-9 of the layer-2 scale (fp16 rounding of y1, of the output, and of the slope constant on the negative branch)."""
+    k, C = 20, 128
+    r = rng(N + 78)
+    pq = r.standard_normal((B * N, 2 * C)).astype(np.float16)
+    idx = r.integers(0, N, (B, N, k)).astype(np.int32)
+    s2, t2 = (r.standard_normal(C).astype(np.float32) for _ in range(2))
+    w2 = (r.standard_normal((C, C)) / np.sqrt(C)).astype(np.float16)
+    P, Q = pq[:, :C].reshape(B, N, C).astype(np.float64), pq[:, C:].reshape(B, N, C).astype(np.float64)
+    y1 = _leaky(P[np.arange(B)[:, None, None], idx] + Q[:, :, None, :])
+    y2 = _leaky((y1 @ w2.astype(np.float64).T) * s2 + t2)
+    x1_ref, x2_ref = y1.max(2).reshape(B * N, C), y2.max(2).reshape(B * N, C)
+    d_pq = torch.from_numpy(pq).cuda()
+    x = torch.zeros(B * N, 4 * C, device="cuda", dtype=torch.float16)
+    ops.edgeconv_dg20_f16(d_pq, 2 * C, d_pq[:, C:], 2 * C, dev(idx, torch.int32), B, N, torch.from_numpy(w2).cuda(), dev(s2), dev(t2),
+                          ops.ACT_LEAKY, 0.01, x, 4 * C, x[:, C:], 4 * C)
+    got = x.float().cpu().numpy()
+    assert np.abs(got[:, :C] - x1_ref).max() <= 2.0 ** -10 * max(1.0, np.abs(x1_ref).max())
+    assert np.abs(got[:, C:2 * C] - x2_ref).max() <= 2.0 ** -9 * np.abs(y2).max()
+    assert (got[:, 2 * C:] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core kNN (exact)
 @pytest.mark.parametrize("variant", [3, 2, 1, 0])
 @pytest.mark.parametrize("B,N,k,kind", [

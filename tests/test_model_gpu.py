@@ -274,6 +274,63 @@ def test_tf32_mode_descriptor_error_bound(cuda, golden, name, B, N, kw):
     assert err <= TF32_TOL, f"{name}: {err:.3e}"
 
 
+# ------------------------------------------------------------------------------------------------ FP16-operand mode
+F16_TOL = 5e-5    # "f16" mode: fp16 activations / operands downstream of the kNN, fp32 accumulation; measured values are printed
+
+
+@pytest.mark.parametrize("name,B,N,kw", [
+    ("c2_lpdnet_eval", 4, 4096, dict(featnet="lpdnet")),
+    ("c2_lpdnet_eval_small", 2, 1024, dict(featnet="lpdnet")),
+    ("c2_lpdnet_tnets_eval", 2, 1024, dict(featnet="lpdnet", feature_transform=True, xyz_trans=True)),
+    ("c2_lpdnetorigin_eval", 2, 4096, dict(featnet="lpdnetorigin")),      # no f16 kernels for this featnet: behaves as tf32
+])
+def test_f16_mode_descriptor_error_bound(cuda, golden, name, B, N, kw):
+    """ops.set_precision("f16"): descriptors against the UNMODIFIED reference's fp32 goldens.  For featnet=lpdnet the fp16 kernels
+    must actually run (labels checked) and the error must stay below F16_TOL — tighter than the tf32 mode's measured 4-9e-5,
+    because fp16 operands are rounded to nearest (11 significant bits) where kind::tf32 truncates to 10."""
+    g = golden(name)
+    model, _ = build(g, num_points=N, emb_dims=1024, **kw)
+    x = synth.clouds(B, N).cuda()
+    prev = ops.set_precision("f16")
+    try:
+        ops.profile(True)
+        with torch.no_grad():
+            out = model(x).cpu().numpy()
+        labels = [l for l, _, _ in ops.profile(False)]
+        with torch.no_grad():
+            again = model(x).cpu().numpy()
+    finally:
+        ops.set_precision(prev)
+    err = np.abs(out - g["out"]).max()
+    print(f"\n[f16] {name}: max-abs descriptor error {err:.3e} (|out|max {np.abs(g['out']).max():.3f})")
+    assert np.array_equal(out, again), "f16 mode must be deterministic"
+    if kw["featnet"] == "lpdnet":
+        for want in ("lpd_edgeconv_dg_f16[128x128]", "lpd_gemm_f16[", "lpd_gemm_f16_tn["):
+            assert any(l.startswith(want) for l in labels), (want, labels)
+        assert err <= F16_TOL, f"{name}: {err:.3e}"
+    else:
+        assert err <= TF32_TOL, f"{name}: {err:.3e}"
+
+
+def test_f16_mode_through_the_embedding_driver(cuda, golden):
+    """get_latent_vectors in f16 mode: graph replay == eager, and switching the precision mode re-captures the graph"""
+    g = golden("c2_lpdnet_eval_small")
+    model, _ = build(g, num_points=1024, emb_dims=1024, featnet="lpdnet")
+    x = synth.clouds(10, 1024, seed=5)
+    prev = ops.set_precision("f16")
+    try:
+        with torch.no_grad():
+            want16 = model(x.cuda()).cpu().numpy()
+        got16 = evaluate.get_latent_vectors(model, x[:, 0].numpy(), batch_num=3)
+        ops.set_precision("tf32")
+        with torch.no_grad():
+            want32 = model(x.cuda()).cpu().numpy()
+        got32 = evaluate.get_latent_vectors(model, x[:, 0].numpy(), batch_num=3)
+    finally:
+        ops.set_precision(prev)
+    assert np.array_equal(got16, want16) and np.array_equal(got32, want32) and not np.array_equal(want16, want32)
+
+
 def test_database_sharded_retrieval_merge_is_bit_exact(cuda):
     """C4 big-database variant: rows split into 3 shards, per-shard exact top-25 with global indices, lpd_topk_merge ->
     identical (indices AND fp64 distances) to the unsharded search, including ties across a shard boundary."""
