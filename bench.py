@@ -679,10 +679,11 @@ def bench_train(ctx):
         nparams = sum(p.numel() for p in model.parameters())
         res = {"metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": ctx.steps, "warmup": ctx.warmup,
                "ms_per_step": t_ms / ctx.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+               "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
                "config": {"workload": "C3: LPD-Net training step (train-mode forward, lazy quadruplet loss m1=0.5 m2=0.2, backward, "
                                       "gradient all-reduce, fused Adam), 2 tuples = 44 x 4096-pt submaps per GPU per step",
-                          "precision": args.precision, "submaps_per_gpu_per_step": TRAIN_CLOUDS, "tuples_per_gpu": TRAIN_BQ, "points": NPTS,
+                          "precision": "fp32" if args.precision == "fp32" else "tf32 tensor-core GEMMs (the training path has no f16 form)",
+                          "submaps_per_gpu_per_step": TRAIN_CLOUDS, "tuples_per_gpu": TRAIN_BQ, "points": NPTS,
                           "sharding": f"whole tuples per GPU (dp{ctx.world}), per-rank BatchNorm statistics; gradients: {opt.describe_reduction()} "
                                       f"({4 * nparams / 1e6:.1f} MB fp32 per step)",
                           "l2": "256 MiB memset between timed steps (untimed); 4 rotating tuple batches", "last_loss": last_loss},
