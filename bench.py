@@ -163,8 +163,8 @@ def roofline_of(label, ms_total, launches, step_ms, peaks, B, N=NPTS, k=KNN):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons of ONE GPU during the timed region, sampled in-process through NVML from a thread
-    (rank 0 only: eight ranks each forking `nvidia-smi -lms 20` was a measurable part of the 8-GPU straggling in round 1)."""
+    """SM clock, power, temperature and throttle reasons of this rank's GPU during the timed region, sampled in-process through
+    NVML from a thread (round 1 forked one `nvidia-smi -lms 20` per rank: eight concurrent 50 Hz driver queries)."""
     REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index: int, enable: bool = True, period_s: float = 0.01):
@@ -179,9 +179,14 @@ class ClockSampler:
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            sm, reasons = [], set()
+            sm, reasons, power, temp = [], set(), [], []
             while True:
                 sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    temp.append(pynvml.nvmlDeviceGetTemperature(h, pynvml.NVML_TEMPERATURE_GPU))
+                except Exception:  # noqa: BLE001
+                    pass
                 mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for name, bit in self.REASONS.items():
@@ -189,8 +194,9 @@ class ClockSampler:
                         reasons.add(name)
                 if self._stop.wait(self.period):
                     break
-            self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(mx), "reasons": sorted(reasons), "samples": len(sm),
-                           "how": "NVML in-process, rank 0"}
+            self.result = {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": float(mx), "reasons": sorted(reasons),
+                           "samples": len(sm), "power_w_max": max(power) if power else None, "temp_c_max": max(temp) if temp else None,
+                           "how": "NVML in-process thread"}
         except Exception as ex:  # noqa: BLE001 — NVML missing / not permitted: fall back to one nvidia-smi query
             self.result = self._smi_once(str(ex))
 
@@ -293,6 +299,20 @@ class Ctx:
         per_step = [s.elapsed_time(e) for s, e in evs]
         mine = sum(per_step)
         return self.max_over_ranks(mine), self.gather_floats(mine), per_step
+
+    def rank_report(self, per_step, clk):
+        """per-rank diagnostics gathered on rank 0: [min, median, max] step time and the GPU's clocks / power during the region.
+        A rank whose MINIMUM step time is high runs on a slower GPU (clocks, power cap); a high maximum alone is a straggling step."""
+        mine = {"rank": self.rank, "gpu": self.local, "step_ms_min_median_max": [round(min(per_step), 4), round(statistics.median(per_step), 4),
+                                                                                 round(max(per_step), 4)],
+                "step_ms": [round(v, 3) for v in per_step],
+                "sm_mhz_median": clk.get("sm_mhz"), "sm_mhz_min": clk.get("sm_min_mhz"), "power_w_max": clk.get("power_w_max"),
+                "temp_c_max": clk.get("temp_c_max"), "reasons": clk.get("reasons")}
+        if self.world == 1:
+            return [mine]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, mine)
+        return out
 
     def timed_region(self, fn):
         """one CUDA-event pair around fn() (end-to-end regions that synchronise inside) -> ms, max over ranks"""
@@ -532,10 +552,11 @@ def bench_embed(ctx, tag: str):
 
     for i in range(ctx.warmup):
         step(i)
-    with ClockSampler(ctx.local, enable=ctx.rank == 0) as clk:
+    with ClockSampler(ctx.local) as clk:
         t_ms, per_rank, per_step = ctx.timed_steps(step)
     value = ctx.world * B * ctx.steps / (t_ms * 1e-3)
     launches = step_graph.launches * ctx.steps
+    ranks = ctx.rank_report(per_step, clk.result)
 
     # ---- end to end through the public API: PINNED host clouds -> H2D -> descriptors -> D2H into host memory ----
     big = torch.cat([h[:, 0] for h in host], 0).pin_memory()            # [4*B, N, 3]
@@ -580,8 +601,7 @@ def bench_embed(ctx, tag: str):
                           "launch": "each timed step = D2D copy of the step's input + ONE CUDA-graph replay of the eager kernel sequence",
                           "l2": "256 MiB memset between timed steps (untimed); 4 rotating input batches; intermediates > 1 GiB/step"},
                "clocks": clk.result, "gpu_launches": launches,
-               "per_rank_ms_per_step": [round(v / ctx.steps, 4) for v in per_rank],
-               "step_ms_min_median_max_rank0": [round(min(per_step), 4), round(statistics.median(per_step), 4), round(max(per_step), 4)],
+               "per_rank_ms_per_step": [round(v / ctx.steps, 4) for v in per_rank], "ranks": ranks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N * 3 * 4, "d2h_bytes_per_step": B * 256 * 4,
                        "api": "lpdnet_b200.evaluate.get_latent_vectors (pinned host clouds -> H2D -> graph replay -> D2H host descriptors)"},
                "roofline": roofline_of(top, tot[top], cnt[top], step_ms, ctx.peaks, B, N, k), "rooflines": rooflines,
@@ -632,11 +652,12 @@ def bench_train(ctx):
         step(i)
     ctx.barrier()
     ops.reset_launch_count()
-    with ClockSampler(ctx.local, enable=ctx.rank == 0) as clk:
+    with ClockSampler(ctx.local) as clk:
         t_ms, per_rank, per_step = ctx.timed_steps(step)
     launches = ops.launch_count()
     value = ctx.world * TRAIN_CLOUDS * ctx.steps / (t_ms * 1e-3)
     last_loss = float(state["loss"])
+    ranks = ctx.rank_report(per_step, clk.result)
 
     # ---- end to end: pinned host tuples -> H2D -> step -> loss value back on the host, every step ----
     def e2e():
@@ -688,7 +709,7 @@ def bench_train(ctx):
                                       f"({4 * nparams / 1e6:.1f} MB fp32 per step)",
                           "l2": "256 MiB memset between timed steps (untimed); 4 rotating tuple batches", "last_loss": last_loss},
                "clocks": clk.result, "gpu_launches": launches,
-               "per_rank_ms_per_step": [round(v / ctx.steps, 4) for v in per_rank],
+               "per_rank_ms_per_step": [round(v / ctx.steps, 4) for v in per_rank], "ranks": ranks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TRAIN_CLOUDS * NPTS * 3 * 4, "d2h_bytes_per_step": 4,
                        "api": "lpdnet_b200.train_pointnetvlad.train_step (pinned host tuples -> loss value on the host)",
                        "last_loss": state.get("loss_host")},
@@ -722,7 +743,7 @@ def bench_retrieval(ctx):
     for i in range(ctx.warmup):
         step(i)
     ops.reset_launch_count()
-    with ClockSampler(ctx.local, enable=ctx.rank == 0) as clk:
+    with ClockSampler(ctx.local) as clk:
         t_ms, per_rank, _ = ctx.timed_steps(step)
     launches = ops.launch_count()
     value = searches * ctx.steps / (t_ms * 1e-3)                      # fixed total work: strong scaling

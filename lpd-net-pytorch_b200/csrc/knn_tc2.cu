@@ -55,6 +55,7 @@
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace lpd {
 
@@ -862,12 +863,18 @@ static int make_tmap_f16(CUtensorMap* m, const __half* base, long long rows, int
 
 static inline size_t align_up2(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// candidate slots per (row, column half) for k <= 24.  40 is 1.5 x the ~27 candidates a row collects, but a row whose neighbours
+// pile up in few strided groups gets a loose threshold and now and then (about one row in 3e5 on uniform clouds) collects more than
+// 40 in one half: its 64-row tile then goes to the exact kernel, whose single CTA needs 0.86 ms for the 4096-candidate scan — a
+// 30 % longer step for that batch.  64 slots make the overflow rare enough not to matter (LPD_KNN_CAP=40 restores the old value).
+static int g_cap_small = [] { const char* e = getenv("LPD_KNN_CAP"); return (e && atoi(e) == 40) ? 40 : 64; }();
+
 struct Knn2Ws {
     size_t off_xx, off_nrm, off_sn, off_ext, off_r2, off_r2c, off_mu, off_sc, off_flags, off_xh, off_cnt, off_cand, total;
     int npad, cap;
     Knn2Ws(int B, int N, int k) {
         npad = (N + 255) / 256 * 256;
-        cap = k <= 24 ? 40 : 64;
+        cap = (k <= 24 && g_cap_small == 40) ? 40 : 64;
         size_t o = 0;
         off_xx = o; o = align_up2(o + (size_t)B * npad * 4, 256);
         off_nrm = o; o = align_up2(o + (size_t)B * npad * 4, 256);
@@ -935,8 +942,10 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     P.qtiles = ceil_div(N, mt == 2 ? 256 : 128); P.ctiles = ceil_div(N, K2_C);
     // k <= 24: 40 slots per (row, half), uniform error bound; k <= 32: 64 slots, per-candidate bound
     if (mt == 3) {          // 128 rows per item, query tile in tensor memory (TS-mode MMA)
-        rc = (W.cap == 40) ? knn2_launch<1, 40, false, true>(ta, tb, P, st) : knn2_launch<1, 64, true, true>(ta, tb, P, st);
+        rc = (W.cap == 40) ? knn2_launch<1, 40, false, true>(ta, tb, P, st)
+                           : (k <= 24 ? knn2_launch<1, 64, false, true>(ta, tb, P, st) : knn2_launch<1, 64, true, true>(ta, tb, P, st));
     } else if (W.cap == 40) rc = (mt == 2) ? knn2_launch<2, 40, false>(ta, tb, P, st) : knn2_launch<1, 40, false>(ta, tb, P, st);
+    else if (k <= 24) rc = (mt == 2) ? knn2_launch<2, 64, false>(ta, tb, P, st) : knn2_launch<1, 64, false>(ta, tb, P, st);
     else             rc = (mt == 2) ? knn2_launch<2, 64, true>(ta, tb, P, st) : knn2_launch<1, 64, true>(ta, tb, P, st);
     if (rc != LPD_OK) return rc;
     rc = (W.cap == 40) ? knn2_refine_launch<40>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, st)
