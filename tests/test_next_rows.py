@@ -97,3 +97,48 @@ def test_checkpoint_format_and_scheduler(tmp_path):
     for recall in (50.0, 50.0, 50.0, 50.0):                                    # no improvement for > patience epochs
         sched.step(recall)
     assert abs(opt.param_groups[0]["lr"] - 2e-4) < 1e-12
+
+
+def test_epoch_loop_schedule_on_cpu(tmp_path, monkeypatch):
+    """reference train_pointnetvlad.py:38-170: the loop's schedule — base loader up to epoch 7, the
+    hard-negative loader afterwards with a descriptor refresh at the switch and every 700 (epoch + 1) samples, evaluation +
+    checkpoint + ReduceLROnPlateau after every epoch, resume from a checkpoint.  Host logic only: the step itself is stubbed."""
+    from lpdnet_b200 import train_pointnetvlad as tp
+    calls = {"base": 0, "advance": 0, "update": 0, "eval": 0, "iters": []}
+    model = torch.nn.Linear(4, 4)
+
+    def fake_step(model_, optimizer, q, p, n, o, m1, m2, **kw):
+        assert (m1, m2) == (0.5, 0.2) and kw["use_min"] and kw["lazy"] and not kw["ignore_zero_loss"]
+        calls[q] += 1
+        return torch.tensor(0.25)
+
+    monkeypatch.setattr(tp, "train_step", fake_step)
+    base = [("base",) * 4] * 3
+    advance = [("advance",) * 4] * 800                       # 1600 samples per epoch: crosses 700 * (epoch + 1) multiples
+
+    def update():
+        calls["update"] += 1
+
+    def evaluate_fn(m):
+        calls["eval"] += 1
+        return 10.0, 0.5, 40.0 + calls["eval"]
+
+    logged = []
+    cfg = tp.TrainConfig(max_epoch=10, optimizer="momentum", model_save_path=str(tmp_path))
+    state = tp.train(model, base, advance, evaluate_fn, cfg, update_vectors=update, log=lambda n, v, i: logged.append((n, i)))
+    assert calls["base"] == 3 * 8 and calls["advance"] == 800 * 2 and calls["eval"] == 10
+    # refreshes: one at the switch (epoch 8), then whenever TOTAL_ITERATIONS hits a multiple of 700 * (epoch + 1) (rounded to the batch)
+    iters, expect = 3 * 8 * 2, 1
+    for epoch in (8, 9):
+        for _ in range(800):
+            iters += 2
+            expect += iters % (700 * (epoch + 1) // 2 * 2) == 0
+    assert calls["update"] == expect and state["iter"] == iters and state["epoch"] == 9
+    assert (tmp_path / "9-model.ckpt").exists() and (tmp_path / "best-model.ckpt").exists() and state["best"] == 50.0
+    assert ("Val Recall", 9) in logged and ("Loss", 0) in logged
+    # resume: starts at the epoch after the checkpoint's, keeps the iteration counter
+    calls.update(base=0, advance=0, update=0, eval=0)
+    cfg2 = tp.TrainConfig(max_epoch=11, optimizer="momentum", model_save_path=str(tmp_path), pretrained_path=str(tmp_path / "9-model.ckpt"))
+    state2 = tp.train(model, base, advance, evaluate_fn, cfg2, update_vectors=update)
+    assert calls["base"] == 0 and calls["advance"] == 800 and state2["epoch"] == 10 and state2["iter"] == iters + 1600
+    assert calls["update"] >= 1                               # starting_epoch > DIVISION_EPOCH + 1: refresh before the first step

@@ -345,3 +345,33 @@ def test_tnet_backward_in_isolation(cuda, k):
     for n, p in net.named_parameters():
         r, gm = ref[n], grads.by_param[p].double()
         assert (gm - r).abs().max().item() <= 1e-4 * max(float(r.abs().max()), 1e-2 * gmax), n
+
+
+def test_epoch_loop_runs_end_to_end_on_the_gpu(cuda, tmp_path):
+    """train() (reference train_pointnetvlad.py:38-170) with the real step: two epochs over three tuple batches, evaluation through
+    evaluate.evaluate_model on a small synthetic evaluation set, checkpoints written and loadable, the loss goes down"""
+    from lpdnet_b200 import evaluate, train_pointnetvlad as tp
+    ops.set_precision("fp32")
+    model = build_train(256)
+    g = torch.Generator().manual_seed(3)
+    base = []
+    for i in range(3):
+        x = synth.clouds(22, 256, seed=40 + i).view(1, 22, 256, 3)
+        base.append(tuple(t.contiguous() for t in torch.split(x, [1, 2, 18, 1], dim=1)))
+    places = synth.clouds(12, 256, seed=77)[:, 0]
+    db_clouds = [places.numpy(), (places + 0.01 * torch.randn(places.shape, generator=g)).numpy()]
+    q_clouds = [c[::2].copy() for c in db_clouds]
+    sets = [[{m: [2 * i] for m in range(2)} for i in range(6)] for _ in range(2)]
+    losses = []
+
+    def evaluate_fn(m):
+        return evaluate.evaluate_model(m, db_clouds, q_clouds, sets, batch_num=4)
+
+    cfg = tp.TrainConfig(batch_num_queries=1, max_epoch=2, lr=1e-3, model_save_path=str(tmp_path))
+    state = tp.train(model, base, base, evaluate_fn, cfg, log=lambda n, v, i: losses.append(v) if n == "Loss" else None)
+    assert len(losses) == 6 and all(np.isfinite(losses)) and np.mean(losses[3:]) < np.mean(losses[:3])
+    assert state["epoch"] == 1 and state["iter"] == 6 and 0.0 <= state["recall"] <= 100.0
+    ck = torch.load(tmp_path / "1-model.ckpt", weights_only=False)
+    fresh = PNV.PointNetVlad(num_points=256, featnet="lpdnet", emb_dims=1024).cuda()
+    fresh.load_state_dict(ck["state_dict"], strict=True)
+    assert model.training                                     # evaluate_model leaves the model in train() mode, like the reference
