@@ -182,6 +182,13 @@ int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void* C, int ld
 int lpd_gemm_f16_tn(const void* A, int lda, const void* B, int ldb, float* C, int ldc, long long strideC,
                     int M, int N, int K, int batch, void* stream);
 int lpd_f32_to_f16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols, void* stream);
+/* "3xTF32" operand preparation: x (n contiguous floats) = hi + lo, hi = x truncated to TF32, lo = x - hi; out [3][n] holds
+ * [hi; hi; lo] (role 0, the A side) or [hi; lo; hi] (role 1, the B side), so that one lpd_gemm_tf32_tn contraction over the stacked
+ * rows accumulates hi.hi + hi.lo + lo.hi in fp32.  Used by the NetVLAD hidden projection (65536 x 256, PointNetVlad.py:76), which
+ * stays at fp32 accuracy on the tensor cores in every precision mode but "fp32". */
+int lpd_split3_tf32(const float* x, long long n, float* out, int role, void* stream);
+/* the A side of that projection in one pass: v [B][R] row-major -> out [3][R][Bp] = v transposed, split [hi; hi; lo], Bp % 4 == 0. */
+int lpd_transpose_split3(const float* v, int B, long long R, int Bp, float* out, void* stream);
 /* lpd_gemm_tf32 with the result written as fp16 (C [M][ldc] halves): the projection in front of the f16-mode edge kernels, whose
  * input (the conv2 feature map that also feeds the exact feature-space kNN) stays fp32. */
 int lpd_gemm_tf32_out16(const float* A, int lda, const float* B, int ldb, void* C, int ldc, int M, int N, int K,

@@ -299,8 +299,73 @@ f32_to_f16_kernel(const float* __restrict__ x, long long ldx, __half* __restrict
     }
 }
 
+// x = hi + lo with hi = x truncated to TF32 (exactly what kind::tf32 reads of an fp32 operand) and lo = x - hi (exact in fp32).
+// out holds three stacked copies: role 0 (A side) [hi; hi; lo], role 1 (B side) [hi; lo; hi], so that ONE TF32 contraction over
+// the stacked axis accumulates hi.hi + hi.lo + lo.hi in fp32 ("3xTF32": ~2^-21 relative instead of 2^-10).
+__global__ void __launch_bounds__(256)
+split3_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ out, int role) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float v = x[e];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float lo = v - hi;
+        out[e] = hi;
+        out[n + e] = role ? lo : hi;
+        out[2 * n + e] = role ? hi : lo;
+    }
+}
+
+// the A side of the 3xTF32 hidden projection in one pass: v [B][R] (row-major descriptors) -> out [3][R][Bp] = the TRANSPOSED
+// matrix split into [hi; hi; lo], columns B..Bp-1 zero.  32 x 32 shared-memory tiles: coalesced along R on the way in, along B out.
+__global__ void __launch_bounds__(256)
+transpose_split3_kernel(const float* __restrict__ v, int B, long long R, int Bp, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long r0 = (long long)blockIdx.x * 32;
+    for (int b0 = 0; b0 < Bp; b0 += 32) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = b0 + ty + 8 * i;
+            tile[ty + 8 * i][tx] = (b < B && r0 + tx < R) ? __ldg(v + (size_t)b * R + r0 + tx) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = r0 + ty + 8 * i;
+            const int b = b0 + tx;
+            if (r < R && b < Bp) {
+                const float x = tile[tx][ty + 8 * i];
+                const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+                const size_t o = (size_t)r * Bp + b;
+                out[o] = hi;
+                out[(size_t)R * Bp + o] = hi;
+                out[2 * (size_t)R * Bp + o] = x - hi;
+            }
+        }
+    }
+}
+
 }  // namespace tc
 }  // namespace lpd
+
+extern "C" int lpd_transpose_split3(const float* v, int B, long long R, int Bp, float* out, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(v && out && B >= 1 && R >= 1 && Bp >= B && (Bp % 4) == 0);
+    const long long blocks = (R + 31) / 32;
+    LPD_REQUIRE(blocks <= 0x7fffffffLL);
+    tc::transpose_split3_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(v, B, R, Bp, out);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
+extern "C" int lpd_split3_tf32(const float* x, long long n, float* out, int role, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(x && out && n >= 1 && (role == 0 || role == 1));
+    const long long blocks = (n + 255) / 256;
+    tc::split3_tf32_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, as_stream(stream)>>>(x, n, out, role);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
 
 extern "C" int lpd_f32_to_f16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols, void* stream) {
     using namespace lpd;

@@ -261,6 +261,27 @@ def to_f16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def split3_tf32(x: torch.Tensor, role: int) -> torch.Tensor:
+    """contiguous fp32 [rows, cols] -> [3 * rows, cols]: the TF32 hi / lo split stacked as [hi; hi; lo] (role 0) or [hi; lo; hi]
+    (role 1), see lpd_split3_tf32"""
+    lib = _lib.load()
+    x = _f32(x, "x").contiguous()
+    rows, cols = x.shape
+    out = torch.empty(3 * rows, cols, device=x.device, dtype=torch.float32)
+    _call("lpd_split3_tf32", 1, lib.lpd_split3_tf32, x.data_ptr(), x.numel(), out.data_ptr(), int(role), _stream())
+    return out
+
+
+def transpose_split3(v: torch.Tensor, Bp: int) -> torch.Tensor:
+    """v [B, R] fp32 -> [3 * R, Bp]: v transposed and TF32-split as [hi; hi; lo] (lpd_transpose_split3)"""
+    lib = _lib.load()
+    v = _f32(v, "v").contiguous()
+    B, R = v.shape
+    out = torch.empty(3 * R, Bp, device=v.device, dtype=torch.float32)
+    _call("lpd_transpose_split3", 1, lib.lpd_transpose_split3, v.data_ptr(), B, R, Bp, out.data_ptr(), _stream())
+    return out
+
+
 def _f16(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda or t.dtype != torch.float16:
         raise _lib.LpdError(f"{name} must be a CUDA float16 tensor, got {t.dtype} on {t.device}")

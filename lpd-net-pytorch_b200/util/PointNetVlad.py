@@ -90,6 +90,7 @@ class NetVLADLoupe(nn.Module):
         p["wct"] = ops.transpose(p["wc"].unsqueeze(0))[0]      # [K, D]: K-contiguous operand for the tensor-core path
         if p["wct"].is_cuda:
             p["wct_h"] = ops.to_f16(p["wct"])                  # "f16" precision mode
+            p["wh3"] = ops.split3_tf32(p["wh"], 1)             # TF32 hi / lo split of the hidden weights, stacked [hi; lo; hi]
         if self.add_batch_norm:
             p["s1"], p["t1"] = fold_bn(self.bn1)
         else:
@@ -127,9 +128,19 @@ class NetVLADLoupe(nn.Module):
         while KD % splits:
             splits //= 2
         kc = KD // splits
-        part = torch.empty(splits, B, O, device=f.device, dtype=torch.float32)
-        ops.gemm(v, p["wh"], a_layout=ops.A_MK, b_layout=ops.B_KN, M=B, N=O, K=kc, lda=KD, ldb=O, out=part, ldc=O,
-                 batch=splits, strideA=kc, strideB=kc * O, strideC=B * O)                     # :76
+        if ops.get_precision() != "fp32" and (3 * kc) % 32 == 0 and O % 4 == 0 and O <= 256 and "wh3" in p:
+            # the (K*D) x output_dim projection on the tensor cores at fp32 accuracy ("3xTF32"): out[b][o] = sum_r vT[r][b] W_h[r][o] is
+            # a contraction over the ROWS of two row-major matrices (vT = the transposed descriptors, W_h as stored), both split
+            # into TF32 hi + lo parts stacked along the rows ([hi; hi; lo] x [hi; lo; hi]: hi.hi + hi.lo + lo.hi), cut into
+            # `splits` slices = one tcgen05 tile per CTA; the partial sums are reduced in fixed order with the BatchNorm affine.
+            # (A single-pass TF32 / fp16 projection is 2 x faster still but doubles the descriptor error: this layer feeds a
+            # BatchNorm whose scale amplifies it.)
+            Bp = (B + 3) // 4 * 4
+            part = ops.gemm_tf32_tn(ops.transpose_split3(v, Bp), p["wh3"], M=B, N=O, K=3 * kc, lda=Bp, ldb=O, batch=splits)   # :76
+        else:
+            part = torch.empty(splits, B, O, device=f.device, dtype=torch.float32)
+            ops.gemm(v, p["wh"], a_layout=ops.A_MK, b_layout=ops.B_KN, M=B, N=O, K=kc, lda=KD, ldb=O, out=part, ldc=O,
+                     batch=splits, strideA=kc, strideB=kc * O, strideC=B * O)                 # :76
         h = ops.splitk_reduce(part, splits, B, O, p["s2"], p["t2"])                           # :78
         if self.gating:
             h = self.context_gating(h)                                                        # :80-81
