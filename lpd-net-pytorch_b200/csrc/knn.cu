@@ -63,11 +63,8 @@ __device__ __forceinline__ float knn_sqnorm(const float* __restrict__ t, int p) 
 }
 
 template <int CP>
-__global__ void __launch_bounds__(KNN_THREADS, 2)
-knn_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ idx_out, int idx_i64,
-           const int* __restrict__ tile_flags) {
-    // fallback mode of the tensor-core path: only 64-row tiles flagged as "needs exact recompute" do any work
-    if (tile_flags != nullptr && tile_flags[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;
+__device__ __forceinline__ void knn_tile(const float* __restrict__ x, int N, int C, int k, void* __restrict__ idx_out, int idx_i64,
+                                         const int b, const int tile) {
     extern __shared__ __align__(16) float smem[];
     float* Qs = smem;                      // [CP][QT]
     float* Cs = Qs + CP * KNN_QT;          // [CP][CT]
@@ -77,8 +74,7 @@ knn_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 thread grid: 4 rows x 8 cols each
-    const int b = blockIdx.y;
-    const int q0 = blockIdx.x * KNN_QT;
+    const int q0 = tile * KNN_QT;
     const float* xb = x + (size_t)b * N * C;
 
     knn_load_tile<CP, KNN_QT>(xb, q0, N, C, Qs, tid);
@@ -174,6 +170,29 @@ knn_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ 
             if (idx_i64) reinterpret_cast<long long*>(idx_out)[o] = li[r];
             else reinterpret_cast<int*>(idx_out)[o] = li[r];
         }
+    }
+}
+
+template <int CP>
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ idx_out, int idx_i64,
+           const int* __restrict__ tile_flags) {
+    // fallback mode of the tensor-core path: only 64-row tiles flagged as "needs exact recompute" do any work
+    if (tile_flags != nullptr && tile_flags[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;
+    knn_tile<CP>(x, N, C, k, idx_out, idx_i64, blockIdx.y, blockIdx.x);
+}
+
+// work-list mode: list[0] = number of flagged tiles, list[1 + i] = cloud * tiles_per_cloud + tile.  A small fixed grid walks the
+// list (the usual case is an empty one: a launch of one CTA per tile cost 11 us just to find that out).
+template <int CP>
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_list_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__ idx_out, int idx_i64,
+                const int* __restrict__ list, int tiles_per_cloud) {
+    const int count = list[0];
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        const int t = list[1 + i];
+        knn_tile<CP>(x, N, C, k, idx_out, idx_i64, t / tiles_per_cloud, t % tiles_per_cloud);
+        __syncthreads();                   // the shared-memory tiles are rewritten by the next entry
     }
 }
 
@@ -281,6 +300,16 @@ knn3_kernel(const float* __restrict__ x, int N, int C, int k, void* __restrict__
 
 int knn_simt64_flagged(const float* x, int B, int N, int k, void* idx, int idx_i64, const int* flags, cudaStream_t st) {
     return knn_launch<64>(x, B, N, 64, k, idx, idx_i64, st, flags);
+}
+
+int knn_simt64_list(const float* x, int B, int N, int k, void* idx, int idx_i64, const int* list, cudaStream_t st) {
+    const size_t smem = (size_t)(64 * (KNN_QT + KNN_CT) + KNN_QT * KNN_CT + KNN_QT + KNN_CT) * sizeof(float);
+    LPD_CUDA_CHECK(allow_smem(knn_list_kernel<64>, smem));
+    const int tiles = ceil_div(N, KNN_QT);
+    const long long all = (long long)B * tiles;
+    knn_list_kernel<64><<<(unsigned)(all < 296 ? all : 296), KNN_THREADS, smem, st>>>(x, N, 64, k, idx, idx_i64, list, tiles);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
 }
 
 static int knn3_launch(const float* x, int B, int N, int C, int k, void* idx, int idx_i64, cudaStream_t st) {

@@ -59,7 +59,7 @@
 
 namespace lpd {
 
-int knn_simt64_flagged(const float* x, int B, int N, int k, void* idx, int idx_i64, const int* flags, cudaStream_t st);
+int knn_simt64_list(const float* x, int B, int N, int k, void* idx, int idx_i64, const int* list, cudaStream_t st);
 
 namespace tc {
 
@@ -169,55 +169,74 @@ __host__ __device__ __forceinline__ int inv_mod64(int a) {   // a odd: a*a = 1 (
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// 0a. per cloud: mean feature and fp16 scale.  One 1024-thread block per cloud; fixed summation order (deterministic).
-__global__ void __launch_bounds__(1024)
-knn2_center_kernel(const float* __restrict__ x, int N, float* __restrict__ mu, float* __restrict__ sc) {
-    __shared__ float4 red[1024];
-    __shared__ float4 mus[16];
-    __shared__ float wmax[32];
-    const int b = blockIdx.x, t = threadIdx.x, cg = t & 15, rl = t >> 4;
+// 0a. per cloud: channel sums, minima and maxima.  K2_CSPLIT CTAs per cloud write partial results in a fixed order (no atomics:
+// deterministic); knn2_prep_kernel folds them into the mean feature mu and the power-of-two fp16 scale sigma.
+constexpr int K2_CSPLIT = 8;
+__global__ void __launch_bounds__(256)
+knn2_center_kernel(const float* __restrict__ x, int N, float* __restrict__ part) {
+    __shared__ float4 red[3][256];
+    __shared__ int sbad;
+    const int b = blockIdx.y, sp = blockIdx.x, t = threadIdx.x, cg = t & 15, rl = t >> 4;
+    const int chunk = (N + K2_CSPLIT - 1) / K2_CSPLIT;
+    const int n0 = sp * chunk, n1 = min(N, n0 + chunk);
     const float4* xb = reinterpret_cast<const float4*>(x + (size_t)b * N * 64);
+    if (t == 0) sbad = 0;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int n = rl; n < N; n += 64) {
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    bool bad = false;                      // NaN / inf anywhere in the cloud must not be lost by fminf / fmaxf
+    for (int n = n0 + rl; n < n1; n += 16) {
         const float4 v = __ldg(xb + (size_t)n * 16 + cg);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        lo.x = fminf(lo.x, v.x); lo.y = fminf(lo.y, v.y); lo.z = fminf(lo.z, v.z); lo.w = fminf(lo.w, v.w);
+        hi.x = fmaxf(hi.x, v.x); hi.y = fmaxf(hi.y, v.y); hi.z = fmaxf(hi.z, v.z); hi.w = fmaxf(hi.w, v.w);
+        bad |= !(fabsf(v.x) <= 3.0e38f) || !(fabsf(v.y) <= 3.0e38f) || !(fabsf(v.z) <= 3.0e38f) || !(fabsf(v.w) <= 3.0e38f);
     }
-    red[t] = s;
+    red[0][t] = s; red[1][t] = lo; red[2][t] = hi;
     __syncthreads();
-    for (int o = 512; o >= 16; o >>= 1) {
+    if (bad) sbad = 1;
+    for (int o = 128; o >= 16; o >>= 1) {
         if (t < o) {
-            const float4 a = red[t], c = red[t + o];
-            red[t] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+            const float4 a0 = red[0][t], c0 = red[0][t + o], a1 = red[1][t], c1 = red[1][t + o], a2 = red[2][t], c2 = red[2][t + o];
+            red[0][t] = make_float4(a0.x + c0.x, a0.y + c0.y, a0.z + c0.z, a0.w + c0.w);
+            red[1][t] = make_float4(fminf(a1.x, c1.x), fminf(a1.y, c1.y), fminf(a1.z, c1.z), fminf(a1.w, c1.w));
+            red[2][t] = make_float4(fmaxf(a2.x, c2.x), fmaxf(a2.y, c2.y), fmaxf(a2.z, c2.z), fmaxf(a2.w, c2.w));
         }
         __syncthreads();
     }
+    // partials of this CTA: [3][64] floats (sum, min, max) + the bad flag
+    float* o = part + ((size_t)b * K2_CSPLIT + sp) * 196;
     if (t < 16) {
-        const float inv = 1.f / (float)N;
-        const float4 m = make_float4(red[t].x * inv, red[t].y * inv, red[t].z * inv, red[t].w * inv);
-        mus[t] = m;
-        reinterpret_cast<float4*>(mu + (size_t)b * 64)[t] = m;
+        reinterpret_cast<float4*>(o)[t] = red[0][t];
+        reinterpret_cast<float4*>(o + 64)[t] = red[1][t];
+        reinterpret_cast<float4*>(o + 128)[t] = red[2][t];
     }
-    __syncthreads();
-    const float4 m = mus[cg];
-    float mx = 0.f;
-    for (int n = rl; n < N; n += 64) {
-        const float4 v = __ldg(xb + (size_t)n * 16 + cg);
-        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x - m.x), fabsf(v.y - m.y)), fmaxf(fabsf(v.z - m.z), fabsf(v.w - m.w))));
-    }
-    // NaN / inf anywhere in the cloud must not be lost by fmaxf: carry a flag
-    bool bad = !(mx <= 3.0e38f);
-    for (int n = rl; n < N && !bad; n += 64) {
-        const float4 v = __ldg(xb + (size_t)n * 16 + cg);
-        bad = !(fabsf(v.x) <= 3.0e38f) || !(fabsf(v.y) <= 3.0e38f) || !(fabsf(v.z) <= 3.0e38f) || !(fabsf(v.w) <= 3.0e38f);
-    }
-    if (bad) mx = INFINITY;
+    if (t == 0) o[192] = sbad ? 1.f : 0.f;
+}
+
+// folds the partials of one cloud: mean feature (shared memory, 64 floats) and fp16 scale (sigma, 2 / sigma^2; NaN = unusable cloud).
+// Every CTA of the prep kernel does this redundantly (1.5 K floats out of L2) in the same order: same values everywhere.
+__device__ __forceinline__ void knn2_fold_center(const float* __restrict__ part, int b, int N, float* mus, float* ssc, float* red) {
+    const int t = threadIdx.x;
+    if (t < 64) {
+        const float* pb = part + (size_t)b * K2_CSPLIT * 196;
+        float s = 0.f, lo = INFINITY, hi = -INFINITY, bad = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-    if ((t & 31) == 0) wmax[t >> 5] = mx;
+        for (int sp = 0; sp < K2_CSPLIT; ++sp) {
+            s += pb[sp * 196 + t];
+            lo = fminf(lo, pb[sp * 196 + 64 + t]);
+            hi = fmaxf(hi, pb[sp * 196 + 128 + t]);
+            bad += pb[sp * 196 + 192];
+        }
+        const float m = s * (1.f / (float)N);
+        mus[t] = m;
+        float g = fmaxf(hi - m, m - lo);
+        if (bad != 0.f || !(g <= 3.0e38f)) g = INFINITY;
+        red[t] = g;
+    }
     __syncthreads();
     if (t == 0) {
         float g = 0.f;
-        for (int w = 0; w < 32; ++w) g = fmaxf(g, wmax[w]);
+        for (int c = 0; c < 64; ++c) g = fmaxf(g, red[c]);
         float sigma = 1.f, c2 = 2.f;
         if (g > 0.f) {
             int e;
@@ -230,20 +249,23 @@ knn2_center_kernel(const float* __restrict__ x, int N, float* __restrict__ mu, f
                 c2 = ldexpf(2.f, -2 * se);
             }
         }
-        sc[2 * b] = sigma;
-        sc[2 * b + 1] = c2;
+        ssc[0] = sigma; ssc[1] = c2;
     }
+    __syncthreads();
 }
 
 // 0b. per point: fp16 centred operand row, both norms, per-cloud maxima
 __global__ void __launch_bounds__(256)
-knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ sc, int N, int Npad,
+knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, float* __restrict__ sc, int N, int Npad,
                  __half* __restrict__ xh, uint4* __restrict__ ext, float* __restrict__ xxpad, float* __restrict__ nrmpad,
                  float* __restrict__ snpad, float* __restrict__ r2, float* __restrict__ r2c) {
-    __shared__ float4 mus[16];
+    __shared__ __align__(16) float mus_f[64];
+    __shared__ float ssc[2], sred[64];
     const int b = blockIdx.y;
-    if (threadIdx.x < 16) mus[threadIdx.x] = reinterpret_cast<const float4*>(mu + (size_t)b * 64)[threadIdx.x];
-    __syncthreads();
+    knn2_fold_center(part, b, N, mus_f, ssc, sred);
+    const float4* mus = reinterpret_cast<const float4*>(mus_f);
+    const float sigma = ssc[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc[2 * b] = sigma; sc[2 * b + 1] = ssc[1]; }
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= Npad) return;
     float vxx = INFINITY, vn = INFINITY;
@@ -254,7 +276,6 @@ knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mu, cons
         np = (n & ~63) | (((n & 63) * a + bb) & 63);
     }
     if (n < N) {
-        const float sigma = __ldg(sc + 2 * b);
         const float4* p = reinterpret_cast<const float4*>(x + ((size_t)b * N + n) * 64);
         uint4* o = reinterpret_cast<uint4*>(xh + ((size_t)b * N + np) * 64);
         float acc = 0.f, accc = 0.f;
@@ -285,7 +306,6 @@ knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mu, cons
     //   t_ij = sigma^2 x'_i.x'_j - V_j = (sigma^2 / 2) a_ij,   V = 2^6 B1 + 2^-5 B2 + 2^-14 B3  (three fp16 pieces, residual
     //   < 2^-15), against the constant query-side row [2^6, 2^-5, 2^-14, 2^15, 0...]; slot 3 pushes padded candidates to -2e9.
     {
-        const float sigma = __ldg(sc + 2 * b);
         float b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = -60000.f;
         if (n < N) {
             const float V = 0.5f * (sigma * sigma) * vn;
@@ -741,6 +761,10 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // hit distinct banks).  A lane-per-candidate gather straight from global memory costs up to 32 L1 wavefronts per load
 // instruction and ran at 90 % of the L1 wavefront peak.  The final order is a rank count over 64-bit keys
 // (orderable(pd) << 32 | ~index: larger = better), two keys per LDS.128.
+// a row that cannot be finished here flags its 64-row tile (once) and appends it to the work list of the exact kernel
+__device__ __forceinline__ void knn2_flag_tile(int* __restrict__ flags, int* __restrict__ list, int tile) {
+    if (atomicExch(flags + tile, 1) == 0) list[1 + atomicAdd(list, 1)] = tile;
+}
 constexpr int RF_STRIDE = 36;
 constexpr int RF_WARPS = 8;
 template <int CAP>
@@ -757,7 +781,7 @@ template <int CAP>
 __global__ void __launch_bounds__(RF_WARPS * 32)
 knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad, const int* __restrict__ cnt,
                    const int* __restrict__ cand, int B, int N, int Npad, int k, void* __restrict__ idx_out, int idx_i64,
-                   int* __restrict__ flags) {
+                   int* __restrict__ flags, int* __restrict__ list) {
     using S = RefineSmem<CAP>;
     extern __shared__ __align__(16) uint8_t rsm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -771,7 +795,7 @@ knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad,
     const int c0 = __ldg(cnt + grow * 2), c1 = __ldg(cnt + grow * 2 + 1);
     const int total = c0 + c1;
     if (c0 > CAP || c1 > CAP || total < k) {      // overflow / unusable bound: the exact kernel recomputes the 64-row tile
-        if (lane == 0) flags[(size_t)b * ((N + 63) / 64) + qi / 64] = 1;
+        if (lane == 0) knn2_flag_tile(flags, list, b * ((N + 63) / 64) + qi / 64);
         return;
     }
     const float* xb = x + (size_t)b * N * 64;
@@ -835,13 +859,202 @@ knn2_refine_kernel(const float* __restrict__ x, const float* __restrict__ xxpad,
     }
 }
 
+// 2'. The same refine with the candidate rows fetched by the TMA unit (the default).  In the kernel above every candidate row
+// crosses the LSU three times (LDG.128 into registers, STS.128 into the tile, LDS.128 back out): 290 L1 wavefronts per query
+// row, 61 % of the L1 data-stage peak while 59 % of the warp stalls wait for those gathers.  Here one elected lane issues
+// cp.async.bulk.tensor ... tile::gather4 (UTMALDG.2D.GATHER4): four arbitrary rows of the [B*N][64] fp32 feature map per
+// instruction land in shared memory without touching the LSU, as two half-row tiles [32 candidates][128 B] in the 128-byte
+// swizzle (16-byte chunk ^ (line & 7)), so that "lane = candidate" reads its row with conflict-free LDS.128.  The query row
+// comes with a plain bulk copy on the same mbarrier.  Arithmetic, keys and ranking are those of knn2_refine_kernel: identical
+// output.  Warps are persistent (row = warp + i * warps) and own one mbarrier each.
+template <int CAP, int WARPS>
+struct RefineTmaSmem {
+    static constexpr int KEYS = 2 * CAP + 2;
+    static constexpr size_t rows = (size_t)WARPS * 2 * 32 * 128;                     // per warp: two half-row tiles of 4 KB (1 KB aligned)
+    static constexpr size_t off_xi = rows;                                           // [64] floats per warp
+    static constexpr size_t off_key = off_xi + (size_t)WARPS * 256;
+    static constexpr size_t key_bytes = (KEYS * 8 + 15) / 16 * 16;
+    static constexpr size_t off_id = off_key + (size_t)WARPS * key_bytes;
+    static constexpr size_t off_bar = off_id + (size_t)WARPS * (2 * CAP + 4) * 4;
+    static constexpr size_t total = off_bar + WARPS * 8;
+    static_assert(total <= 227 * 1024, "refine shared memory budget");
+};
+
+__device__ __forceinline__ void tma_gather4_e(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int col, const int4& r) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(col), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_e(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+knn2_refine_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ x, const float* __restrict__ xxpad,
+                       const int* __restrict__ cnt, const int* __restrict__ cand, int B, int N, int Npad, int k,
+                       void* __restrict__ idx_out, int idx_i64, int* __restrict__ flags, int* __restrict__ list) {
+    using S = RefineTmaSmem<CAP, WARPS>;
+    constexpr int IPL = (CAP + 31) / 32;               // list slots per lane and column half
+    extern __shared__ __align__(1024) uint8_t rsm_t[];
+    uint8_t* rsm = rsm_t;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint8_t* s_rows = rsm + (size_t)w * 2 * 32 * 128;
+    const float4* s_xi = reinterpret_cast<const float4*>(rsm + S::off_xi + (size_t)w * 256);
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(rsm + S::off_key + (size_t)w * S::key_bytes);
+    int* s_id = reinterpret_cast<int*>(rsm + S::off_id) + w * (2 * CAP + 4);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(rsm + S::off_bar) + w;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const long long rows_total = (long long)B * N;
+    const long long nw = (long long)gridDim.x * WARPS;
+    uint32_t phase = 0;
+    const int sw = lane & 7;
+    // the list of the NEXT row travels in registers while the current row is processed (counts and both raw half lists: the
+    // slots beyond the counts hold stale workspace bytes and are never used)
+    int nc0 = 0, nc1 = 0, nl0[IPL], nl1[IPL];
+    auto prefetch = [&](long long g) {
+        if (g >= rows_total) return;
+        nc0 = __ldg(cnt + g * 2); nc1 = __ldg(cnt + g * 2 + 1);
+        const int* l0 = cand + (size_t)g * 2 * CAP;
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+            const int s = lane + 32 * i;
+            nl0[i] = s < CAP ? __ldg(l0 + s) : 0;
+            nl1[i] = s < CAP ? __ldg(l0 + CAP + s) : 0;
+        }
+    };
+    long long grow = (long long)blockIdx.x * WARPS + w;
+    prefetch(grow);
+    for (; grow < rows_total; grow += nw) {
+        const int b = (int)(grow / N), qi = (int)(grow % N);
+        const int c0 = nc0, c1 = nc1;
+        const int total = c0 + c1;
+        const bool bad = c0 > CAP || c1 > CAP || total < k;   // overflow / unusable bound: the exact kernel recomputes the 64-row tile
+        const int rbase = b * N;                               // first row of the cloud in the [B*N][64] map
+        if (!bad) {
+#pragma unroll
+            for (int i = 0; i < IPL; ++i) {
+                const int s = lane + 32 * i;
+                if (s < c0) s_id[s] = rbase + nl0[i];
+                if (s < c1) s_id[c0 + s] = rbase + nl1[i];
+            }
+            if (lane < 4) s_id[total + lane] = rbase + qi;     // padding of the last gather4 (a row that is in L2 anyway)
+            if (lane < 2) s_key[total + lane] = 0ull;          // padding keys: worse than anything
+        }
+        __syncwarp();
+        if (bad) {
+            if (lane == 0) knn2_flag_tile(flags, list, b * ((N + 63) / 64) + qi / 64);
+            prefetch(grow + nw);
+            continue;
+        }
+        const float xxi = __ldg(xxpad + (size_t)b * Npad + qi);
+        for (int base = 0; base < total; base += 32) {
+            const int nc = min(32, total - base);
+            const int n4 = (nc + 3) >> 2;
+            mbar_expect_tx_e(bar, (uint32_t)n4 * 1024u + (base == 0 ? 256u : 0u));
+            if (base == 0) bulk_load_e(const_cast<float4*>(s_xi), x + (size_t)grow * 64, 256u, bar);
+            for (int g = 0; g < n4; ++g) {
+                const int4 r = *reinterpret_cast<const int4*>(s_id + base + 4 * g);       // warp broadcast
+                tma_gather4_e(s_rows + g * 512, &tmap_x, bar, 0, r);
+                tma_gather4_e(s_rows + 4096 + g * 512, &tmap_x, bar, 32, r);
+            }
+            const int myrow = lane < nc ? s_id[base + lane] : rbase;
+            const float xxj = __ldg(xxpad + (size_t)b * Npad + (myrow - rbase));
+            if (base == 0) prefetch(grow + nw);        // in flight behind the gathers
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            float dot = 0.f;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+                const float4* rj = reinterpret_cast<const float4*>(s_rows + ph * 4096 + lane * 128);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float4 u = s_xi[ph * 8 + g], v = rj[g ^ sw];
+                    dot = __fmaf_rn(u.x, v.x, dot); dot = __fmaf_rn(u.y, v.y, dot);
+                    dot = __fmaf_rn(u.z, v.z, dot); dot = __fmaf_rn(u.w, v.w, dot);
+                }
+            }
+            if (lane < nc) {
+                const float t = -2.0f * dot;
+                const float pd = __fadd_rn(__fsub_rn(__fsub_rn(-xxj, t), xxi), 0.0f);   // (+ 0: -0.0 and +0.0 must share one key)
+                uint32_t u = __float_as_uint(pd);
+                u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;                  // monotone float -> uint
+                s_key[base + lane] = ((unsigned long long)u << 32) | (uint32_t)(~(myrow - rbase));
+            }
+            __syncwarp();                              // tile consumed (and keys visible) before the next gather overwrites it
+        }
+        const size_t o = (size_t)grow * k;
+        const int npairs = (total + 1) >> 1;
+        for (int base = 0; base < total; base += 32) {
+            const int s = base + lane;
+            const unsigned long long mine = s < total ? s_key[s] : ~0ull;
+            int rank = 0;
+            const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(s_key);
+#pragma unroll 4
+            for (int t = 0; t < npairs; ++t) {
+                const ulonglong2 kk = kp[t];                                 // warp broadcast
+                rank += (kk.x > mine) + (kk.y > mine);
+            }
+            if (s < total && rank < k) {
+                const int id = (int)~(uint32_t)mine;
+                if (idx_i64) reinterpret_cast<long long*>(idx_out)[o + rank] = id;
+                else reinterpret_cast<int*>(idx_out)[o + rank] = id;
+            }
+        }
+        __syncwarp();                                  // keys / ids consumed before the next row rewrites them
+    }
+}
+
+// 1 (default): TMA-gather refine; 0: LSU-gather refine (LPD_KNN_REFINE=0)
+static int g_refine_tma = [] { const char* e = getenv("LPD_KNN_REFINE"); return (e && atoi(e) == 0) ? 0 : 1; }();
+static int g_refine_warps = [] { const char* e = getenv("LPD_KNN_REFINE_WARPS"); return e ? atoi(e) : 22; }();
+
+template <int CAP, int WARPS>
+static int knn2_refine_tma_launch(const float* x, const float* xxpad, const int* cnt, const int* cand, int B, int N, int Npad, int k,
+                                  void* idx, int idx_i64, int* flags, int* list, cudaStream_t st) {
+    CUtensorMap tx;
+    int rc = make_tmap(&tx, x, (long long)B * N, 64, 64, 1);          // box = one half row (32 floats = 128 B), 128B swizzle
+    if (rc != LPD_OK) return rc;
+    const size_t smem = RefineTmaSmem<CAP, WARPS>::total;
+    static int sms = 0, per_sm = 0;                                   // per instantiation; one device model per process
+    if (per_sm == 0) {
+        int dev = 0;
+        LPD_CUDA_CHECK(allow_smem(knn2_refine_tma_kernel<CAP, WARPS>, smem));
+        LPD_CUDA_CHECK(cudaGetDevice(&dev));
+        LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        LPD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, knn2_refine_tma_kernel<CAP, WARPS>, WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    const long long want = ((long long)B * N + WARPS - 1) / WARPS;
+    const long long blocks = want < (long long)sms * per_sm ? want : (long long)sms * per_sm;
+    knn2_refine_tma_kernel<CAP, WARPS><<<(unsigned)blocks, WARPS * 32, smem, st>>>(tx, x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
 template <int CAP>
 static int knn2_refine_launch(const float* x, const float* xxpad, const int* cnt, const int* cand, int B, int N, int Npad, int k,
-                              void* idx, int idx_i64, int* flags, cudaStream_t st) {
+                              void* idx, int idx_i64, int* flags, int* list, cudaStream_t st) {
+    if (g_refine_tma) {
+        if (g_refine_warps == 4) return knn2_refine_tma_launch<CAP, 4>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
+        if (g_refine_warps == 11) return knn2_refine_tma_launch<CAP, 11>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
+        return knn2_refine_tma_launch<CAP, 22>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
+    }
     const size_t smem = RefineSmem<CAP>::total;
     LPD_CUDA_CHECK(allow_smem(knn2_refine_kernel<CAP>, smem));
     const unsigned rblocks = (unsigned)(((long long)B * N + RF_WARPS - 1) / RF_WARPS);
-    knn2_refine_kernel<CAP><<<rblocks, RF_WARPS * 32, smem, st>>>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags);
+    knn2_refine_kernel<CAP><<<rblocks, RF_WARPS * 32, smem, st>>>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }
@@ -870,7 +1083,7 @@ static inline size_t align_up2(size_t v, size_t a) { return (v + a - 1) / a * a;
 static int g_cap_small = [] { const char* e = getenv("LPD_KNN_CAP"); return (e && atoi(e) == 40) ? 40 : 64; }();
 
 struct Knn2Ws {
-    size_t off_xx, off_nrm, off_sn, off_ext, off_r2, off_r2c, off_mu, off_sc, off_flags, off_xh, off_cnt, off_cand, total;
+    size_t off_xx, off_nrm, off_sn, off_ext, off_r2, off_r2c, off_mu, off_sc, off_flags, off_list, off_xh, off_cnt, off_cand, total;
     int npad, cap;
     Knn2Ws(int B, int N, int k) {
         npad = (N + 255) / 256 * 256;
@@ -882,9 +1095,10 @@ struct Knn2Ws {
         off_ext = o; o = align_up2(o + (size_t)B * npad * 32, 256);
         off_r2 = o; o += (size_t)B * 4;
         off_r2c = o; o = align_up2(o + (size_t)B * 4, 256);
-        off_mu = o; o = align_up2(o + (size_t)B * 64 * 4, 256);
+        off_mu = o; o = align_up2(o + (size_t)B * K2_CSPLIT * 196 * 4, 256);      // per-cloud partial sums / minima / maxima
         off_sc = o; o = align_up2(o + (size_t)B * 2 * 4, 256);
         off_flags = o; o = align_up2(o + (size_t)B * ((N + 63) / 64) * 4, 256);
+        off_list = o; o = align_up2(o + ((size_t)B * ((N + 63) / 64) + 1) * 4, 256);     // work list of the exact kernel
         off_xh = o; o = align_up2(o + (size_t)B * N * 64 * 2, 256);
         off_cnt = o; o = align_up2(o + (size_t)B * N * 2 * 4, 256);
         off_cand = o; o = align_up2(o + (size_t)B * N * 2 * cap * 4, 256);
@@ -921,11 +1135,11 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     float* mu = reinterpret_cast<float*>(ws + W.off_mu);
     float* sc = reinterpret_cast<float*>(ws + W.off_sc);
     int* flags = reinterpret_cast<int*>(ws + W.off_flags);
+    int* list = reinterpret_cast<int*>(ws + W.off_list);
     __half* xh = reinterpret_cast<__half*>(ws + W.off_xh);
-    const int ftiles = (N + 63) / 64;
     LPD_CUDA_CHECK(cudaMemsetAsync(r2, 0, W.off_mu - W.off_r2, st));     // r2 and r2c
-    LPD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)B * ftiles * sizeof(int), st));
-    knn2_center_kernel<<<B, 1024, 0, st>>>(x, N, mu, sc);
+    LPD_CUDA_CHECK(cudaMemsetAsync(flags, 0, W.off_list - W.off_flags + sizeof(int), st));   // the flags and the list length
+    knn2_center_kernel<<<dim3(K2_CSPLIT, B), 256, 0, st>>>(x, N, mu);
     LPD_LAUNCH_CHECK();
     knn2_prep_kernel<<<dim3(ceil_div(W.npad, 256), B), 256, 0, st>>>(x, mu, sc, N, W.npad, xh, reinterpret_cast<uint4*>(ws + W.off_ext), xxpad, nrmpad, snpad, r2, r2c);
     LPD_LAUNCH_CHECK();
@@ -948,10 +1162,10 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     else if (k <= 24) rc = (mt == 2) ? knn2_launch<2, 64, false>(ta, tb, P, st) : knn2_launch<1, 64, false>(ta, tb, P, st);
     else             rc = (mt == 2) ? knn2_launch<2, 64, true>(ta, tb, P, st) : knn2_launch<1, 64, true>(ta, tb, P, st);
     if (rc != LPD_OK) return rc;
-    rc = (W.cap == 40) ? knn2_refine_launch<40>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, st)
-                       : knn2_refine_launch<64>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, st);
+    rc = (W.cap == 40) ? knn2_refine_launch<40>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, list, st)
+                       : knn2_refine_launch<64>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, list, st);
     if (rc != LPD_OK) return rc;
-    return knn_simt64_flagged(x, B, N, k, idx, idx_i64, flags, st);   // exact recompute of flagged 64-row tiles only
+    return knn_simt64_list(x, B, N, k, idx, idx_i64, list, st);       // exact recompute of the flagged 64-row tiles only
 }
 
 // diagnostics for the tests / tools: where the tile flags of the last run live inside the workspace
