@@ -132,4 +132,65 @@ __device__ __forceinline__ void warp_sort_desc(float (&v)[E], int (&id)[E], int 
     }
 }
 
+// ---- in-register bitonic networks over 32 values per THREAD (every index is a compile-time constant after unrolling) ----
+__device__ __forceinline__ void cex_desc(float& a, float& b) {   // a >= b afterwards
+    const float hi = fmaxf(a, b), lo = fminf(a, b);
+    a = hi; b = lo;
+}
+__device__ __forceinline__ void merge32_desc(float (&v)[32]) {    // bitonic sequence -> descending
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if ((i & stride) == 0) cex_desc(v[i], v[i | stride]);
+    }
+}
+__device__ __forceinline__ void sort32_desc(float (&v)[32]) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if ((i & stride) == 0) {
+                    const bool desc = ((i & size) == 0) || (size == 32);
+                    if (desc) cex_desc(v[i], v[i | stride]); else cex_desc(v[i | stride], v[i]);
+                }
+            }
+        }
+    }
+}
+// the same with an index payload and the canonical total order: (a, ia) before (b, ib) when a > b, or a == b and ia < ib
+__device__ __forceinline__ bool kv_before(float a, int ia, float b, int ib) { return (a > b) || (a == b && ia < ib); }
+__device__ __forceinline__ void cex_desc_kv(float& a, int& ia, float& b, int& ib) {   // (a, ia) before (b, ib) afterwards
+    const bool swap = kv_before(b, ib, a, ia);
+    const float ta = swap ? b : a, tb = swap ? a : b;
+    const int tia = swap ? ib : ia, tib = swap ? ia : ib;
+    a = ta; b = tb; ia = tia; ib = tib;
+}
+__device__ __forceinline__ void merge32_desc_kv(float (&v)[32], int (&id)[32]) {
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if ((i & stride) == 0) cex_desc_kv(v[i], id[i], v[i | stride], id[i | stride]);
+    }
+}
+__device__ __forceinline__ void sort32_desc_kv(float (&v)[32], int (&id)[32]) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if ((i & stride) == 0) {
+                    const bool desc = ((i & size) == 0) || (size == 32);
+                    if (desc) cex_desc_kv(v[i], id[i], v[i | stride], id[i | stride]);
+                    else cex_desc_kv(v[i | stride], id[i | stride], v[i], id[i]);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace lpd
