@@ -119,6 +119,9 @@ def kernel_work(label: str, B: int, N: int = NPTS, k: int = KNN):
     if label.startswith("lpd_edge_gather_ext"):
         C = int(label.split("C=")[1].rstrip("]"))
         return 0.0, 4.0 * B * N * (2 * C + C + k)
+    if label.startswith("lpd_gemm_softmax64["):
+        M, Nn, K = (int(v) for v in label[label.index("[") + 1:-1].split("x"))
+        return 2.0 * M * Nn * K, 2.0 * (M * K + Nn * K + M * Nn)                                  # fp16 in, fp16 assignment out
     if label == "lpd_netvlad_assign":
         return 2.0 * N * 1024 * 64 * B, 4.0 * B * N * (1024 + 64)
     if label.startswith("lpd_conv3_vlad"):
@@ -512,7 +515,8 @@ FAMILIES = {   # kernel-label prefix -> family of the step (SURVEY §8d stages)
     "EdgeConv DG1+DG2": ("lpd_edgeconv_dg",),
     "EdgeConv SN1 gather": ("lpd_edge_gather_ext",),
     "NetVLAD (assign, aggregate, norms, hidden, gating)": ("lpd_netvlad", "lpd_softmax64", "lpd_splitk_reduce", "lpd_gemm_tf32_tn[1024x64",
-                                                           "lpd_gemm_f16_tn[1024x64", "lpd_gemm[", "lpd_conv3_vlad", "lpd_hidden"),
+                                                           "lpd_gemm_f16_tn[1024x64", "lpd_gemm[", "lpd_conv3_vlad", "lpd_hidden", "lpd_gemm_softmax64", "lpd_gemm_f16[262144x64", "lpd_gemm_tf32[262144x64",
+                                                           "lpd_gemm_tf32_tn[64x256", "lpd_transpose_split3"),
 }
 
 

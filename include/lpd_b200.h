@@ -276,6 +276,26 @@ int lpd_softmax64(float* a, long long M, void* stream);
 int lpd_netvlad_finish(float* vlad, const float* a, const float* wc2, int B, int N, int D, int K,
                        float* asum_ws, void* stream);
 
+/* The soft assignment in ONE launch (PointNetVlad.py:48-59): a = softmax_k(scale[k] * (x . Wc)[m][k] + shift[k]) as the epilogue
+ * of the tensor-core GEMM (x [M][lda] fp16 when a_f16 else fp32 consumed as TF32, W = cluster_weights^T [64][ldw] of the same
+ * type; fp32 accumulation).  Writes a32 [M][64] fp32 and / or a16 [M][64] fp16 (either may be NULL, not both) and, when apart is
+ * not NULL, apart[m / 32][64] = the column sums of every block of 32 rows (fp32 values; apart holds ceil(M / 32) * 64 floats;
+ * with max_samples % 32 == 0 these are per-cloud partial sums of a_sum, PointNetVlad.py:61).  Requires sm_100. */
+int lpd_gemm_softmax64(const void* A, int a_f16, int lda, const void* W, int ldw, int M, int K, const float* scale,
+                       const float* shift, float* a32, void* a16, float* apart, void* stream);
+
+/* lpd_netvlad_finish on given partial sums: apart [B][nparts][K] (sum over nparts = a_sum).  One thread-block cluster of 8 CTAs
+ * per cloud; requires D % 128 == 0 and D <= 1024.  Replaces PointNetVlad.py:61-74. */
+int lpd_netvlad_finish_parts(float* vlad, const float* apart, int nparts, const float* wc2, int B, int D, int K, void* stream);
+
+/* Tail of NetVLAD + context gating in one launch (PointNetVlad.py:76-81, 103-115):
+ *     h[b][o] = s2[o] * sum_s part[s][b][o] + t2[o]                       (split-K partial sums of v . hidden1_weights, bn2 folded)
+ *     out[b][o] = h[b][o] * sigmoid(sg[o] * sum_i h[b][i] wg[i][o] + tg[o])   (gating_weights [O][O] as stored; sg / tg = folded bn1 or
+ *                                                                           NULL / gating_biases)
+ * O <= 1024; s2, t2, sg, tg may be NULL. */
+int lpd_hidden_gate(const float* part, int splits, int B, int O, const float* s2, const float* t2, const float* wg,
+                    const float* sg, const float* tg, float* out, void* stream);
+
 /* deterministic split-K reduce + affine: out[m][n] = scale[n]*sum_s part[s][m][n] + shift[n]
  * (second half of the 65536->256 hidden projection + bn2, PointNetVlad.py:76-78) */
 int lpd_splitk_reduce(const float* part, int splits, int M, int N, const float* scale,

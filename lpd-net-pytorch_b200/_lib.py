@@ -62,6 +62,9 @@ SIGNATURES = {
     "lpd_softmax64": (_i, [_vp, _ll, _vp]),
     "lpd_netvlad_finish": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "lpd_splitk_reduce": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "lpd_gemm_softmax64": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lpd_netvlad_finish_parts": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "lpd_hidden_gate": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lpd_quadruplet_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lpd_retrieval_workspace_bytes": (_sz, [_i, _i, _i]),
     "lpd_retrieval_topk": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -39,6 +39,9 @@ struct Params {
     int batch; long long strideC;   // TN: slice z contracts rows [z*K, (z+1)*K) of both operands into C + z*strideC
     int bM, bN;                     // !TN, batch > 1: slice z multiplies rows [z*bM, ..) of A with rows [z*bN, ..) of B into C rows z*bM ..
     int accumulate;                 // !TN: C += result (the epilogue reads C)
+    // EPI == 1 (BN == 64): row softmax of the affine result instead of the activation; C (fp32, may be null), a_h (fp16 copy, may
+    // be null) and apart[row block of 32][64] = the column sums of every 32-row block (may be null)
+    __half* a_h; float* apart;
 };
 
 // TN == false:  C[m][n] = sum_k A[m][k] B[n][k]      (both operands K-contiguous: "K-major" UMMA tiles)
@@ -72,7 +75,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_h(uint32_t smem_addr) {
     return d;
 }
 
-template <int BN, int STAGES, bool TN, typename TIN = float, bool OUT_HALF = false>
+template <int BN, int STAGES, bool TN, typename TIN = float, bool OUT_HALF = false, int EPI = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
     constexpr bool HALF = sizeof(TIN) == 2;
@@ -88,6 +91,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* xch = reinterpret_cast<float*>(tmem_slot + 2);       // EPI == 1: [2][4 quarters][2 halves][32 rows] row max / row sum
+    static_assert(EPI == 0 || (BN == 64 && !TN && !OUT_HALF), "the softmax epilogue covers one 64-column tile");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + BKE - 1) / BKE;
@@ -186,6 +191,64 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const int row0 = m0 + q * 32;
+            if constexpr (EPI == 1) {
+                // softmax over the 64 columns of a row (NetVLAD soft assignment, PointNetVlad.py:48-59): lane = row; this warp holds
+                // columns half*32 .. +31 of its 32 rows, the partner warp (same lane quarter) the other 32: row maximum and row sum
+                // are exchanged through shared memory behind a 64-thread named barrier.
+                if (row0 < p.M) {
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * 32, r);
+                    float v[32];
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = half * 32 + j;
+                        const float sc = p.scale ? __ldg(p.scale + col) : 1.f, sh = p.shift ? __ldg(p.shift + col) : 0.f;
+                        v[j] = fmaf(__uint_as_float(r[j]), sc, sh);
+                        mx = fmaxf(mx, v[j]);
+                    }
+                    float* xmax = xch, *xsum = xch + 256;
+                    xmax[(q * 2 + half) * 32 + lane] = mx;
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                    mx = fmaxf(mx, xmax[(q * 2 + (half ^ 1)) * 32 + lane]);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { v[j] = expf(v[j] - mx); sum += v[j]; }
+                    xsum[(q * 2 + half) * 32 + lane] = sum;
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                    const float tot = xsum[(q * 2) * 32 + lane] + xsum[(q * 2 + 1) * 32 + lane];   // same order in both warps
+                    float* dst = stg + lane * 32;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 2)) =
+                            make_float4(v[4 * j] / tot, v[4 * j + 1] / tot, v[4 * j + 2] / tot, v[4 * j + 3] / tot);
+                    __syncwarp();
+                    const int col = half * 32 + ch * 4;
+                    const size_t goff = (size_t)row0 * 64 + col;
+                    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + rsub;
+                        const float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + ((ch ^ (rr & 7)) << 2));
+                        if (row0 + rr < p.M) {
+                            cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+                            if (p.C) *reinterpret_cast<float4*>(p.C + goff + (size_t)rr * 64) = o;
+                            if (p.a_h) {
+                                const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                                *reinterpret_cast<uint2*>(p.a_h + goff + (size_t)rr * 64) =
+                                    make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                            }
+                        }
+                    }
+                    // column sums of the 32-row block: rows rsub, rsub + 4, ... were added above; now across the four rsub lanes
+                    cs.x += __shfl_down_sync(kFull, cs.x, 16); cs.y += __shfl_down_sync(kFull, cs.y, 16);
+                    cs.z += __shfl_down_sync(kFull, cs.z, 16); cs.w += __shfl_down_sync(kFull, cs.w, 16);
+                    cs.x += __shfl_down_sync(kFull, cs.x, 8); cs.y += __shfl_down_sync(kFull, cs.y, 8);
+                    cs.z += __shfl_down_sync(kFull, cs.z, 8); cs.w += __shfl_down_sync(kFull, cs.w, 8);
+                    if (p.apart && lane < 8) *reinterpret_cast<float4*>(p.apart + (size_t)(row0 >> 5) * 64 + col) = cs;
+                    __syncwarp();
+                }
+            } else {
 #pragma unroll 1
             for (int i = 0; i < CPW; ++i) {
                 const int c = half * CPW + i;
@@ -244,6 +307,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 __syncwarp();                            // staging buffer is rewritten by the next chunk
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -258,10 +322,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 }
 
-template <int BN, int STAGES, bool TN = false, typename TIN = float, bool OUT_HALF = false>
+template <int BN, int STAGES, bool TN = false, typename TIN = float, bool OUT_HALF = false, int EPI = 0>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + EPI_WARPS * 32 * 32 * 4 + 256;
-    LPD_CUDA_CHECK(allow_smem(gemm_tf32_kernel<BN, STAGES, TN, TIN, OUT_HALF>, smem));
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + EPI_WARPS * 32 * 32 * 4 + 256 + (EPI == 1 ? 2048 : 0);
+    LPD_CUDA_CHECK(allow_smem(gemm_tf32_kernel<BN, STAGES, TN, TIN, OUT_HALF, EPI>, smem));
     int dev = 0, sms = 0;
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -269,7 +333,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaSt
     p.tiles_n = ceil_div(p.N, BN);
     const long long tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_tf32_kernel<BN, STAGES, TN, TIN, OUT_HALF><<<grid, THREADS, smem, st>>>(ta, tb, p);
+    gemm_tf32_kernel<BN, STAGES, TN, TIN, OUT_HALF, EPI><<<grid, THREADS, smem, st>>>(ta, tb, p);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }
@@ -400,7 +464,7 @@ extern "C" int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void
     tc::Params p;
     p.C = reinterpret_cast<float*>(C); p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = scale; p.shift = shift;
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
-    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0;
+    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
     if (out_half) {
         if (BN == 64) return tc::launch<64, 8, false, __half, true>(ta, tb, p, st);
@@ -434,7 +498,7 @@ extern "C" int lpd_gemm_f16_tn(const void* A, int lda, const void* B, int ldb, f
     if (rc != LPD_OK) return rc;
     tc::Params p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = nullptr; p.shift = nullptr; p.neg_slope = 1.f;
-    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = strideC; p.bM = p.bN = 0; p.accumulate = 0;
+    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = strideC; p.bM = p.bN = 0; p.accumulate = 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
     if (BN == 64) return tc::launch<64, 8, true, __half>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6, true, __half>(ta, tb, p, st);
@@ -466,7 +530,7 @@ extern "C" int lpd_gemm_tf32_ex(const float* A, int lda, const float* B, int ldb
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = scale; p.shift = shift;
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
     p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = 0;
-    p.bM = batch > 1 ? M : 0; p.bN = batch > 1 ? N : 0; p.accumulate = accumulate ? 1 : 0;
+    p.bM = batch > 1 ? M : 0; p.bN = batch > 1 ? N : 0; p.accumulate = accumulate ? 1 : 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
     if (BN == 64) return tc::launch<64, 8>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6>(ta, tb, p, st);
@@ -494,7 +558,7 @@ extern "C" int lpd_gemm_tf32_out16(const float* A, int lda, const float* B, int 
     tc::Params p;
     p.C = reinterpret_cast<float*>(C); p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = scale; p.shift = shift;
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
-    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0;
+    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
     if (BN == 64) return tc::launch<64, 8, false, float, true>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6, false, float, true>(ta, tb, p, st);
@@ -529,9 +593,36 @@ extern "C" int lpd_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb
     if (rc != LPD_OK) return rc;
     tc::Params p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.scale = nullptr; p.shift = nullptr; p.neg_slope = 1.f;
-    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = strideC; p.bM = p.bN = 0; p.accumulate = 0;
+    p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = strideC; p.bM = p.bN = 0; p.accumulate = 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
     if (BN == 64) return tc::launch<64, 8, true>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6, true>(ta, tb, p, st);
     return tc::launch<256, 4, true>(ta, tb, p, st);
+}
+
+extern "C" int lpd_gemm_softmax64(const void* A, int a_f16, int lda, const void* W, int ldw, int M, int K, const float* scale,
+                                  const float* shift, float* a32, void* a16, float* apart, void* stream) {
+    using namespace lpd;
+    LPD_REQUIRE(A && W && M >= 1 && K >= 1 && (a32 || a16));
+    LPD_REQUIRE(lda >= K && ldw >= K);
+    const int al = a_f16 ? 8 : 4;
+    LPD_REQUIRE((lda % al) == 0 && (ldw % al) == 0);
+    LPD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)a32 & 15) == 0 && ((uintptr_t)a16 & 7) == 0 &&
+                ((uintptr_t)apart & 15) == 0);
+    int dev = 0, major = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return LPD_EUNSUPPORTED;
+    CUtensorMap ta, tb;
+    int rc = a_f16 ? tc::make_tmap_h(&ta, A, M, K, lda, tc::BM) : tc::make_tmap(&ta, reinterpret_cast<const float*>(A), M, K, lda, tc::BM);
+    if (rc != LPD_OK) return rc;
+    rc = a_f16 ? tc::make_tmap_h(&tb, W, 64, K, ldw, 64) : tc::make_tmap(&tb, reinterpret_cast<const float*>(W), 64, K, ldw, 64);
+    if (rc != LPD_OK) return rc;
+    tc::Params p;
+    p.C = a32; p.ldc = 64; p.M = M; p.N = 64; p.K = K; p.scale = scale; p.shift = shift; p.neg_slope = 1.f;
+    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0;
+    p.a_h = reinterpret_cast<__half*>(a16); p.apart = apart;
+    cudaStream_t st = as_stream(stream);
+    if (a_f16) return tc::launch<64, 8, false, __half, false, 1>(ta, tb, p, st);
+    return tc::launch<64, 8, false, float, false, 1>(ta, tb, p, st);
 }

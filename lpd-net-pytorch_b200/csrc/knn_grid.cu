@@ -568,30 +568,36 @@ knn_grid_lockstep_kernel(const float4* __restrict__ sorted, const int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Rescue of a SHORT list (the usual case: 2-3 % of the queries): one warp per listed query, brute force over the whole cloud,
-// so it needs no box argument at all.  The thread-per-query kernel is a ~50 us serial job per query and a short list leaves
-// 30 of its 32 lanes idle (0.14 ms for 7.6 k queries); a warp finishes a query in ~2.5 k instructions (N = 4096).
-//   pass 1   lane l scores candidates l, l + 32, ... and keeps the maxima of its even and odd rounds: 64 strided group maxima;
-//            tau = the largest group maximum that at least k group maxima reach (a lower bound of the k-th best score);
+// Rescue of a SHORT list (the usual case: ~5 % of the queries, mostly in boundary cells where the k-th neighbour lies beyond the
+// +-1 box): one warp per listed query.  The thread-per-query kernel is a ~50 us serial job per query and a short list leaves 30
+// of its 32 lanes idle (0.14 ms for 13 k queries).  The warp first searches the +-2 cell box of the query (25 contiguous ranges
+// of the cell-ordered cloud) with the same sufficiency test as above and, if that fails, the whole cloud (no box argument at all):
+//   pass 1   lane l scores candidates l, l + 32, ... of every range and keeps the maxima of its even and odd rounds: 64 strided
+//            group maxima; tau = the largest group maximum that at least k group maxima reach (a lower bound of the k-th best);
 //   pass 2   the same scores again; everything >= tau is appended to a shared-memory list by ballot compaction;
 //   rank     entry e's output position = the number of listed entries before it in the canonical order (keys are distinct:
 //            the original index breaks ties); positions < k are written.
-// A list that overflows (masses of exact ties) is replaced by k rounds of "best entry after the previous output" over the
-// whole cloud: slow, always correct.
+// A whole-cloud list that overflows (masses of exact ties) is replaced by k rounds of "best entry after the previous output":
+// slow, always correct.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int RW_WARPS = 4;
 constexpr int RW_LIST = 128;
+constexpr int RW_R = 2;                                   // box radius in cells
+constexpr int RW_RANGES = (2 * RW_R + 1) * (2 * RW_R + 1);
 
 __global__ void __launch_bounds__(RW_WARPS * 32)
-knn_xyz_rescue_warp_kernel(const float4* __restrict__ sorted, const int* __restrict__ sidx, int N, int k,
-                           void* __restrict__ idx_out, int idx_i64, const int* __restrict__ rlist, int rlimit) {
+knn_xyz_rescue_warp_kernel(const float4* __restrict__ sorted, const int* __restrict__ sidx, const int* __restrict__ cell_start,
+                           const GridHeader* __restrict__ hdr, int N, int k, void* __restrict__ idx_out, int idx_i64,
+                           const int* __restrict__ rlist, int rlimit) {
     __shared__ float lvs[RW_WARPS][RW_LIST];
     __shared__ int lis[RW_WARPS][RW_LIST];
+    __shared__ int2 rngs[RW_WARPS][RW_RANGES];
     const int count = rlist[0];
     if (count > rlimit) return;                            // long list: the thread-per-query kernel takes it
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* lv = lvs[w];
     int* li = lis[w];
+    int2* rng = rngs[w];
     const unsigned lt = (1u << lane) - 1u;
     const int nwarps = gridDim.x * RW_WARPS;
 #pragma unroll 1
@@ -600,94 +606,189 @@ knn_xyz_rescue_warp_kernel(const float4* __restrict__ sorted, const int* __restr
         const int b = g / N, t = g - b * N;
         const float4* so = sorted + (size_t)b * N;
         const int* si = sidx + (size_t)b * N;
+        const int* cs = cell_start + (size_t)b * (GRID_MAX_G * GRID_MAX_G * GRID_MAX_G + 1);
+        const GridHeader h = hdr[b];
+        const int G = h.G;
         const float4 q = so[t];
         const size_t o = ((size_t)b * N + si[t]) * k;
-        // ---- pass 1: 64 strided group maxima ----
-        float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 2
-        for (int p = lane; p < N; p += 64) {
-            const float4 c0 = __ldg(so + p);
-            m0 = fmaxf(m0, canonical_pd(q.x, q.y, q.z, q.w, c0.x, c0.y, c0.z, -c0.w));
-            if (p + 32 < N) {
-                const float4 c1 = __ldg(so + p + 32);
-                m1 = fmaxf(m1, canonical_pd(q.x, q.y, q.z, q.w, c1.x, c1.y, c1.z, -c1.w));
-            }
+        const int cx = cell_coord(q.x, h.minx, h.invhx, G), cy = cell_coord(q.y, h.miny, h.invhy, G), cz = cell_coord(q.z, h.minz, h.invhz, G);
+        const int x0 = max(cx - RW_R, 0), x1 = min(cx + RW_R, G - 1), y0 = max(cy - RW_R, 0), y1 = min(cy + RW_R, G - 1),
+                  z0 = max(cz - RW_R, 0), z1 = min(cz + RW_R, G - 1);
+        float dmin2;
+        {
+            float dmin = INFINITY;
+            if (x0 > 0) dmin = fminf(dmin, q.x - (h.minx + x0 * h.hx));
+            if (x1 < G - 1) dmin = fminf(dmin, (h.minx + (x1 + 1) * h.hx) - q.x);
+            if (y0 > 0) dmin = fminf(dmin, q.y - (h.miny + y0 * h.hy));
+            if (y1 < G - 1) dmin = fminf(dmin, (h.miny + (y1 + 1) * h.hy) - q.y);
+            if (z0 > 0) dmin = fminf(dmin, q.z - (h.minz + z0 * h.hz));
+            if (z1 < G - 1) dmin = fminf(dmin, (h.minz + (z1 + 1) * h.hz) - q.z);
+            dmin = fmaxf(0.f, dmin - h.slack);
+            dmin2 = dmin * dmin;                           // (+inf when the box is the whole grid)
         }
-        float tau = -INFINITY;
+        bool done = false;
 #pragma unroll 1
-        for (int src = 0; src < 32; ++src) {
-            const float v0 = __shfl_sync(kFull, m0, src), v1 = __shfl_sync(kFull, m1, src);
-            const int c0 = __popc(__ballot_sync(kFull, m0 >= v0)) + __popc(__ballot_sync(kFull, m1 >= v0));
-            const int c1 = __popc(__ballot_sync(kFull, m0 >= v1)) + __popc(__ballot_sync(kFull, m1 >= v1));
-            if (c0 >= k) tau = fmaxf(tau, v0);
-            if (c1 >= k) tau = fmaxf(tau, v1);
-        }
-        // ---- pass 2: collect everything at or above tau ----
-        int cnt = 0;
-        __syncwarp();
-#pragma unroll 2
-        for (int base = 0; base < N; base += 32) {
-            const int p = base + lane;
-            bool pass = false;
-            float pd = 0.f;
-            if (p < N) {
-                const float4 c = __ldg(so + p);
-                pd = canonical_pd(q.x, q.y, q.z, q.w, c.x, c.y, c.z, -c.w);
-                pass = pd >= tau;
-            }
-            const unsigned bal = __ballot_sync(kFull, pass);
-            const int pos = cnt + __popc(bal & lt);
-            if (pass && pos < RW_LIST) { lv[pos] = pd; li[pos] = __ldg(si + p); }
-            cnt += __popc(bal);
-        }
-        __syncwarp();
-        if (cnt <= RW_LIST) {
-            // ---- rank by counting ----
-#pragma unroll 1
-            for (int e = lane; e < cnt; e += 32) {
-                const float v = lv[e];
-                const int j = li[e];
-                int rank = 0;
-#pragma unroll 4
-                for (int f = 0; f < cnt; ++f) rank += kv_before(lv[f], li[f], v, j) ? 1 : 0;
-                if (rank < k) {
-                    if (idx_i64) reinterpret_cast<long long*>(idx_out)[o + rank] = j;
-                    else reinterpret_cast<int*>(idx_out)[o + rank] = j;
+        for (int attempt = 0; attempt < 2 && !done; ++attempt) {
+            // ---- the candidate ranges: the rows of the box, or the whole cloud.  The ranges are laid end to end on one flat index
+            //      f (rs[r] = start - first flat index, pe[r] = one past the last flat index of range r), so that a warp iteration
+            //      covers 128 consecutive candidates with four independent loads in flight per lane whatever the range lengths
+            //      (the search is a latency chain of L2 loads: 25 short ranges walked one by one took 13 us per query) ----
+            int nr, total;
+            __syncwarp();
+            {
+                int start = 0, len = 0;
+                if (attempt == 0) {
+                    const int ny = y1 - y0 + 1;
+                    nr = ny * (z1 - z0 + 1);
+                    if (lane < nr) {
+                        const int row = ((z0 + lane / ny) * G + y0 + lane % ny) * G;
+                        start = cs[row + x0];
+                        len = cs[row + x1 + 1] - start;
+                    }
+                } else {
+                    nr = 1;
+                    if (lane == 0) len = N;
                 }
-            }
-        } else {
-            // ---- overflow: k rounds of "best entry strictly after the previous output" ----
-            float pv = INFINITY;
-            int pi = -1;
-#pragma unroll 1
-            for (int outp = 0; outp < k; ++outp) {
-                float bv = -INFINITY;
-                int bi = INT_MAX;
-#pragma unroll 1
-                for (int p = lane; p < N; p += 32) {
-                    const float4 c = __ldg(so + p);
-                    const float v = canonical_pd(q.x, q.y, q.z, q.w, c.x, c.y, c.z, -c.w);
-                    const int j = __ldg(si + p);
-                    const bool after_prev = (v < pv) || (v == pv && j > pi);
-                    if (after_prev && kv_before(v, j, bv, bi)) { bv = v; bi = j; }
-                }
+                int incl = len;
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) {
-                    const float ov = __shfl_xor_sync(kFull, bv, s);
-                    const int oi = __shfl_xor_sync(kFull, bi, s);
-                    if (kv_before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const int up = __shfl_up_sync(kFull, incl, sft);
+                    if (lane >= sft) incl += up;
                 }
-                pv = bv; pi = bi;
-                if (lane == 0) {
-                    if (idx_i64) reinterpret_cast<long long*>(idx_out)[o + outp] = bi;
-                    else reinterpret_cast<int*>(idx_out)[o + outp] = bi;
+                total = __shfl_sync(kFull, incl, 31);
+                if (lane < nr) rng[lane] = make_int2(start - (incl - len), incl);      // (rs, pe)
+            }
+            __syncwarp();
+            if (total < k && attempt == 0) continue;       // fewer than k points in the box
+            // ---- pass 1: 64 strided group maxima ----
+            float m0 = -INFINITY, m1 = -INFINITY;
+            {
+                int rc = 0;
+#pragma unroll 1
+                for (int f0 = 0; f0 < total; f0 += 128) {
+                    float4 c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int f = f0 + 32 * u + lane;
+                        c[u] = make_float4(0.f, 0.f, 0.f, INFINITY);                  // (xx = +inf: score -inf)
+                        if (f < total) {
+                            while (f >= rng[rc].y) ++rc;
+                            c[u] = __ldg(so + f + rng[rc].x);
+                        }
+                    }
+                    m0 = fmaxf(m0, fmaxf(canonical_pd(q.x, q.y, q.z, q.w, c[0].x, c[0].y, c[0].z, -c[0].w),
+                                         canonical_pd(q.x, q.y, q.z, q.w, c[2].x, c[2].y, c[2].z, -c[2].w)));
+                    m1 = fmaxf(m1, fmaxf(canonical_pd(q.x, q.y, q.z, q.w, c[1].x, c[1].y, c[1].z, -c[1].w),
+                                         canonical_pd(q.x, q.y, q.z, q.w, c[3].x, c[3].y, c[3].z, -c[3].w)));
                 }
+            }
+            float tau = -INFINITY;
+#pragma unroll 1
+            for (int src = 0; src < 32; ++src) {
+                const float v0 = __shfl_sync(kFull, m0, src), v1 = __shfl_sync(kFull, m1, src);
+                const int c0 = __popc(__ballot_sync(kFull, m0 >= v0)) + __popc(__ballot_sync(kFull, m1 >= v0));
+                const int c1 = __popc(__ballot_sync(kFull, m0 >= v1)) + __popc(__ballot_sync(kFull, m1 >= v1));
+                if (c0 >= k) tau = fmaxf(tau, v0);
+                if (c1 >= k) tau = fmaxf(tau, v1);
+            }
+            // ---- pass 2: collect everything at or above tau ----
+            int cnt = 0;
+            {
+                int rc = 0;
+#pragma unroll 1
+                for (int f0 = 0; f0 < total; f0 += 128) {
+                    float4 c[4];
+                    int pp[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int f = f0 + 32 * u + lane;
+                        c[u] = make_float4(0.f, 0.f, 0.f, INFINITY);
+                        pp[u] = -1;
+                        if (f < total) {
+                            while (f >= rng[rc].y) ++rc;
+                            pp[u] = f + rng[rc].x;
+                            c[u] = __ldg(so + pp[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float pd = canonical_pd(q.x, q.y, q.z, q.w, c[u].x, c[u].y, c[u].z, -c[u].w);
+                        const bool pass = pp[u] >= 0 && pd >= tau;
+                        const unsigned bal = __ballot_sync(kFull, pass);
+                        const int pos = cnt + __popc(bal & lt);
+                        if (pass && pos < RW_LIST) { lv[pos] = pd; li[pos] = __ldg(si + pp[u]); }
+                        cnt += __popc(bal);
+                    }
+                }
+            }
+            __syncwarp();
+            if (cnt <= RW_LIST) {
+                // ---- rank by counting; in the box attempt the k-th score must not reach the nearest interior face ----
+                int rk[RW_LIST / 32], jj[RW_LIST / 32];
+                float kth = -INFINITY;
+#pragma unroll
+                for (int u = 0; u < RW_LIST / 32; ++u) {
+                    const int e = lane + 32 * u;
+                    rk[u] = INT_MAX; jj[u] = 0;
+                    if (e < cnt) {
+                        const float v = lv[e];
+                        const int j = li[e];
+                        int rank = 0;
+#pragma unroll 4
+                        for (int f = 0; f < cnt; ++f) rank += kv_before(lv[f], li[f], v, j) ? 1 : 0;
+                        rk[u] = rank; jj[u] = j;
+                        if (rank == k - 1) kth = v;            // the k-th best score of the list
+                    }
+                }
+                bool ok = true;
+                if (attempt == 0) {
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) kth = fmaxf(kth, __shfl_xor_sync(kFull, kth, sft));
+                    ok = dmin2 > -kth + h.margin;              // (false when cnt < k: kth stays -inf)
+                }
+                if (ok) {
+#pragma unroll
+                    for (int u = 0; u < RW_LIST / 32; ++u)
+                        if (rk[u] < k) {
+                            if (idx_i64) reinterpret_cast<long long*>(idx_out)[o + rk[u]] = jj[u];
+                            else reinterpret_cast<int*>(idx_out)[o + rk[u]] = jj[u];
+                        }
+                    done = true;
+                }
+            } else if (attempt == 1) {
+                // ---- overflow on the whole cloud: k rounds of "best entry strictly after the previous output" ----
+                float pv = INFINITY;
+                int pi = -1;
+#pragma unroll 1
+                for (int outp = 0; outp < k; ++outp) {
+                    float bv = -INFINITY;
+                    int bi = INT_MAX;
+#pragma unroll 1
+                    for (int p = lane; p < N; p += 32) {
+                        const float4 c = __ldg(so + p);
+                        const float v = canonical_pd(q.x, q.y, q.z, q.w, c.x, c.y, c.z, -c.w);
+                        const int j = __ldg(si + p);
+                        const bool after_prev = (v < pv) || (v == pv && j > pi);
+                        if (after_prev && kv_before(v, j, bv, bi)) { bv = v; bi = j; }
+                    }
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) {
+                        const float ov = __shfl_xor_sync(kFull, bv, sft);
+                        const int oi = __shfl_xor_sync(kFull, bi, sft);
+                        if (kv_before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                    }
+                    pv = bv; pi = bi;
+                    if (lane == 0) {
+                        if (idx_i64) reinterpret_cast<long long*>(idx_out)[o + outp] = bi;
+                        else reinterpret_cast<int*>(idx_out)[o + outp] = bi;
+                    }
+                }
+                done = true;
             }
         }
         __syncwarp();
     }
 }
-
 
 // 1: lock-step search + rescue kernels (default); 0: thread-per-query search only (LPD_KNN_GRID_LOCKSTEP=0)
 static int g_grid_lockstep = [] { const char* e = getenv("LPD_KNN_GRID_LOCKSTEP"); return (e && atoi(e) == 0) ? 0 : 1; }();
@@ -737,7 +838,7 @@ extern "C" int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int i
         knn_grid_lockstep_kernel<<<lgrid, GL_WARPS * 32, 0, st>>>(sorted, sidx, cell_start, hdr, N, k, idx, idx_i64, rlist);
         LPD_LAUNCH_CHECK();
         rlimit = (int)(((long long)B * N) / 8);
-        knn_xyz_rescue_warp_kernel<<<148 * 8, RW_WARPS * 32, 0, st>>>(sorted, sidx, N, k, idx, idx_i64, rlist, rlimit);
+        knn_xyz_rescue_warp_kernel<<<148 * 16, RW_WARPS * 32, 0, st>>>(sorted, sidx, cell_start, hdr, N, k, idx, idx_i64, rlist, rlimit);
         LPD_LAUNCH_CHECK();
         const long long all = ((long long)B * N + GRID_Q_THREADS - 1) / GRID_Q_THREADS;
         grid = dim3((unsigned)(all < 592 ? all : 592), 1);   // a fixed grid walks the list (it returns at once when the list is short)

@@ -434,6 +434,36 @@ def netvlad_finish(vlad, a, wc2, B, N, D, K=64):
     return vlad.view(B, D * K)
 
 
+def gemm_softmax64(x, wct, *, M, K, scale=None, shift=None, want32=True, want16=False, want_parts=False):
+    """soft assignment in one launch: softmax over the 64 clusters as the epilogue of the tensor-core GEMM x [M, K] . wct [64, K]^T
+    (both fp16, or both fp32 consumed as TF32).  Returns (a32 | None, a16 | None, apart [ceil(M/32), 64] | None)."""
+    lib = _lib.load()
+    f16 = x.dtype == torch.float16
+    (_f16 if f16 else _f32)(x, "x"), (_f16 if f16 else _f32)(wct, "wct")
+    a32 = torch.empty(M, 64, device=x.device, dtype=torch.float32) if want32 else None
+    a16 = torch.empty(M, 64, device=x.device, dtype=torch.float16) if want16 else None
+    apart = torch.empty((M + 31) // 32, 64, device=x.device, dtype=torch.float32) if want_parts else None
+    _call(f"lpd_gemm_softmax64[{M}x64x{K}]", 1, lib.lpd_gemm_softmax64, x.data_ptr(), int(f16), K, wct.data_ptr(), K, M, K, _p(scale), _p(shift),
+          _p(a32), _p(a16), _p(apart), _stream())
+    return a32, a16, apart
+
+
+def netvlad_finish_parts(vlad, apart, nparts, wc2, B, D, K=64):
+    """netvlad_finish on given partial column sums of the assignment, apart [B, nparts, K]; in place on vlad [B, D, K]"""
+    lib = _lib.load()
+    _call("lpd_netvlad_finish", 1, lib.lpd_netvlad_finish_parts, vlad.data_ptr(), apart.data_ptr(), nparts, wc2.data_ptr(), B, D, K, _stream())
+    return vlad.view(B, D * K)
+
+
+def hidden_gate(part, splits, B, O, s2, t2, wg, sg, tg):
+    """split-K reduce of the hidden projection + bn2 + context gating in one launch -> [B, O]"""
+    lib = _lib.load()
+    out = torch.empty(B, O, device=part.device, dtype=torch.float32)
+    _call("lpd_hidden_gate", 1, lib.lpd_hidden_gate, part.data_ptr(), splits, B, O, _p(s2), _p(t2), wg.data_ptr(), _p(sg), _p(tg),
+          out.data_ptr(), _stream())
+    return out
+
+
 def splitk_reduce(part, splits, M, N, scale=None, shift=None):
     lib = _lib.load()
     out = torch.empty(M, N, device=part.device, dtype=torch.float32)

@@ -106,11 +106,21 @@ class NetVLADLoupe(nn.Module):
         p = self._prep.get(self, self._build)
         N, D, K, O = self.max_samples, self.feature_size, self.cluster_size, self.output_dim
         M = B * N
+        # softmax (and the 32-row partial sums of a_sum) as the epilogue of the assignment GEMM; the cluster finish kernel takes the partials
+        fused = N % 32 == 0 and D % 128 == 0 and D <= 1024 and M >= 128
+        apart = None
         if f.dtype == torch.float16:                                                          # "f16" mode: F arrives as fp16
-            a, a_h = ops.softmax64_f16(ops.gemm_f16(f, p["wct_h"], M=M, N=K, K=D, scale=p["s1"], shift=p["t1"]), M)   # :48-59
+            if fused:
+                a, a_h, apart = ops.gemm_softmax64(f, p["wct_h"], M=M, K=D, scale=p["s1"], shift=p["t1"], want32=False, want16=True,
+                                                   want_parts=True)                           # :48-59
+            else:
+                a, a_h = ops.softmax64_f16(ops.gemm_f16(f, p["wct_h"], M=M, N=K, K=D, scale=p["s1"], shift=p["t1"]), M)
             vraw = ops.gemm_f16_tn(f, a_h, M=D, N=K, K=N, lda=D, ldb=K, batch=B)              # :64-66 -> [B, D, K]
         elif ops.get_precision() != "fp32" and M >= 128 and D % 4 == 0:                       # :48-59
-            a = ops.softmax64(ops.gemm_tf32(f, p["wct"], M=M, N=K, K=D, scale=p["s1"], shift=p["t1"]), M)
+            if fused:
+                a, _, apart = ops.gemm_softmax64(f, p["wct"], M=M, K=D, scale=p["s1"], shift=p["t1"], want_parts=True)
+            else:
+                a = ops.softmax64(ops.gemm_tf32(f, p["wct"], M=M, N=K, K=D, scale=p["s1"], shift=p["t1"]), M)
         else:
             a = ops.netvlad_assign(f, M, D, p["wc"], p["s1"], p["t1"], K)
         if f.dtype == torch.float16:
@@ -122,7 +132,10 @@ class NetVLADLoupe(nn.Module):
                             strideA=N * D, strideB=N * K)
         if B == 1:
             vraw = vraw.view(1, D, K)
-        v = ops.netvlad_finish(vraw, a, p["wc2"], B, N, D, K)                                 # :61-62,:68-74 -> [B, D*K]
+        if apart is not None:
+            v = ops.netvlad_finish_parts(vraw, apart, N // 32, p["wc2"], B, D, K)             # :61-62,:68-74 -> [B, D*K]
+        else:
+            v = ops.netvlad_finish(vraw, a, p["wc2"], B, N, D, K)
         KD = D * K
         splits = self.HIDDEN_SPLITS
         while KD % splits:
@@ -141,6 +154,9 @@ class NetVLADLoupe(nn.Module):
             part = torch.empty(splits, B, O, device=f.device, dtype=torch.float32)
             ops.gemm(v, p["wh"], a_layout=ops.A_MK, b_layout=ops.B_KN, M=B, N=O, K=kc, lda=KD, ldb=O, out=part, ldc=O,
                      batch=splits, strideA=kc, strideB=kc * O, strideC=B * O)                 # :76
+        if self.gating and O <= 1024:                                                         # :78-81 in one launch
+            g = self.context_gating._prep.get(self.context_gating, self.context_gating._build)
+            return ops.hidden_gate(part, splits, B, O, p["s2"], p["t2"], g["w"], g["s"], g["t"])
         h = ops.splitk_reduce(part, splits, B, O, p["s2"], p["t2"])                           # :78
         if self.gating:
             h = self.context_gating(h)                                                        # :80-81

@@ -269,6 +269,66 @@ def test_netvlad_assign_and_finish(cuda):
     assert np.abs(out.cpu().numpy() - v).max() < 1e-6
 
 
+@pytest.mark.parametrize("f16", [False, True])
+@pytest.mark.parametrize("B,N,D", [(3, 256, 1024), (2, 96, 128), (5, 160, 512)])
+def test_netvlad_fused_assign_softmax_and_cluster_finish(cuda, f16, B, N, D):
+    """lpd_gemm_softmax64 (softmax + 32-row partial sums as the GEMM epilogue, ragged last tile) and lpd_netvlad_finish_parts (cluster
+    kernel) against a float64 restatement of PointNetVlad.py:48-74"""
+    r = rng(11)
+    K, M = 64, B * N
+    x = r.standard_normal((M, D)).astype(np.float32)
+    wc = (r.standard_normal((D, K)) / np.sqrt(D)).astype(np.float32)
+    wc2 = (r.standard_normal((D, K)) / np.sqrt(D)).astype(np.float32)
+    s, t = (1.0 + 0.3 * r.standard_normal(K)).astype(np.float32), r.standard_normal(K).astype(np.float32)
+    if f16:
+        xd, wd = dev(x).half(), dev(wc.T.copy()).half()
+        xr, wr = xd.float().cpu().numpy().astype(np.float64), wd.float().cpu().numpy().astype(np.float64).T
+        tol = 2e-6
+    else:
+        xd, wd = dev(x), dev(wc.T.copy())
+        xr, wr = x.astype(np.float64), wc.astype(np.float64)
+        tol = 2e-3          # TF32 operands
+    z = (xr @ wr) * s + t
+    a_ref = np.exp(z - z.max(1, keepdims=True))
+    a_ref /= a_ref.sum(1, keepdims=True)
+    a32, a16, apart = ops.gemm_softmax64(xd, wd, M=M, K=D, scale=dev(s), shift=dev(t), want32=True, want16=True, want_parts=True)
+    got = a32.cpu().numpy()
+    assert np.abs(got - a_ref).max() < tol
+    assert np.abs(got.sum(1) - 1.0).max() < 1e-5
+    assert np.abs(a16.float().cpu().numpy() - got).max() <= 2.0 ** -11          # fp16 copy of the same values
+    nb = (M + 31) // 32
+    want_parts = np.stack([got[i * 32:(i + 1) * 32].astype(np.float64).sum(0) for i in range(nb)])
+    assert np.abs(apart.cpu().numpy() - want_parts).max() < 1e-5
+    # finish on the partials == finish on the assignment (old path) == float64 restatement
+    a3 = got.reshape(B, N, K).astype(np.float64)
+    vraw = np.einsum("bnd,bnk->bdk", x.reshape(B, N, D).astype(np.float64), a3)
+    v = vraw - a3.sum(1)[:, None, :] * wc2[None]
+    v = v / np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-12)
+    v = v.reshape(B, D * K)
+    v = v / np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-12)
+    out = ops.netvlad_finish_parts(dev(vraw.astype(np.float32)), apart, N // 32, dev(wc2), B, D, K)
+    assert np.abs(out.cpu().numpy() - v).max() < 1e-6
+    out2 = ops.netvlad_finish(dev(vraw.astype(np.float32)), a32, dev(wc2), B, N, D, K)
+    assert np.abs(out2.cpu().numpy() - v).max() < 1e-6
+
+
+def test_hidden_gate_matches_split_reduce_plus_gating(cuda):
+    """lpd_hidden_gate == lpd_splitk_reduce + the gating GEMM (PointNetVlad.py:76-81, 103-115) against float64"""
+    r = rng(12)
+    for B, O, splits in ((64, 256, 128), (3, 100, 7), (1, 1024, 2)):
+        part = r.standard_normal((splits, B, O)).astype(np.float32)
+        s2, t2, sg, tg = (r.standard_normal(O).astype(np.float32) for _ in range(4))
+        wg = (r.standard_normal((O, O)) / np.sqrt(O)).astype(np.float32)
+        h = part.astype(np.float64).sum(0) * s2 + t2
+        want = h / (1.0 + np.exp(-((h @ wg.astype(np.float64)) * sg + tg)))
+        got = ops.hidden_gate(dev(part), splits, B, O, dev(s2), dev(t2), dev(wg), dev(sg), dev(tg)).cpu().numpy()
+        assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+        got2 = ops.hidden_gate(dev(part), splits, B, O, None, None, dev(wg), None, dev(tg)).cpu().numpy()
+        h2 = part.astype(np.float64).sum(0)
+        want2 = h2 / (1.0 + np.exp(-((h2 @ wg.astype(np.float64)) + tg)))
+        assert np.abs(got2 - want2).max() < 2e-5 * max(1.0, np.abs(want2).max())
+
+
 # ------------------------------------------------------------------------------------------------ loss
 def test_loss_forward_backward_vs_reference_golden(cuda, golden):
     g = golden("loss")
