@@ -124,6 +124,13 @@ int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int idx_i64, voi
 int lpd_cell_order(const float* x, int B, int N, int32_t* perm, int32_t* inv, float* xyz_sorted,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* lpd_cell_order that also leaves in `workspace` the search grid of the RE-ORDERED cloud xyz_sorted (required), and the kNN of that
+ * cloud on that grid: lpd_knn_xyz(xyz_sorted, ...) without the second counting sort (a cloud in cell order is its own sort).
+ * The workspace must stay untouched between the two calls.  Same result as lpd_knn_xyz, bit for bit. */
+int lpd_cell_order_grid(const float* x, int B, int N, int32_t* perm, int32_t* inv, float* xyz_sorted,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int lpd_knn_xyz_ordered(int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * General fp32 GEMM with fused per-column affine + activation epilogue (CUDA-core FFMA path,
  * "strict" fp32 arithmetic):

@@ -37,6 +37,8 @@ SIGNATURES = {
     "lpd_knn_xyz_workspace_bytes": (_sz, [_i, _i]),
     "lpd_knn_xyz": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "lpd_cell_order": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lpd_cell_order_grid": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lpd_knn_xyz_ordered": (_i, [_i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "lpd_gemm": (_i, [_vp, _i, _i, _ll, _vp, _i, _i, _ll, _vp, _i, _ll, _i, _i, _i, _i,
                       _vp, _vp, _i, _f, _vp, _vp]),
     "lpd_gemm_tf32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp]),

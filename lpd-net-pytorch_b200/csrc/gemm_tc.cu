@@ -21,6 +21,7 @@
 // bits, vs the 10-bit TRUNCATION kind::tf32 applies to fp32 operands), twice the tensor rate and half the operand bytes.
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace lpd {
 namespace tc {
@@ -353,6 +354,208 @@ static int make_tmap_h(CUtensorMap* m, const void* base, long long rows, int col
     return LPD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-PAIR form of the fp16 GEMM (cta_group::2) for the wide layers (N % 256 == 0, fp16 output: conv3 512 -> 1024 and the 128 ->
+// 512 neighbour / centre projections of the f16 eval path).  In the single-CTA kernel above a 128 x 256 tile needs 4 KB of A and
+// 8 KB of B out of shared memory per 128-clk MMA (96 B/clk) while TMA writes the same 96 B/clk and the fp32 staging of the epilogue
+// adds 64 B/clk: 256 B/clk against the SM's 128 B/clk, which is exactly the 50 % tensor-pipe activity ncu shows for conv3.  Here the
+// two CTAs of a cluster form ONE 256 x 256 tile: each CTA holds 128 rows of A and 128 of the 256 rows of W per stage (TMA ... .cta_group::2
+// signalling the leader's mbarrier), the leader's elected lane issues tcgen05.mma.cta_group::2 (M = 256: each SM multiplies its A
+// half with BOTH W halves), tcgen05.commit ... .multicast::cluster releases the ring slot / hands over the accumulator in both CTAs,
+// and each CTA's epilogue drains its own 128 x 256 accumulator (TMEM -> affine + activation -> fp16 -> 4 KB staging -> full 128-byte
+// lines).  Per SM: 64 B/clk operand reads + 64 B/clk TMA + 32 B/clk staging.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int H2_STAGES = 5;
+constexpr uint32_t H2_A_BYTES = 128 * 128, H2_B_BYTES = 128 * 128, H2_STAGE_BYTES = H2_A_BYTES + H2_B_BYTES;
+constexpr size_t H2_SMEM = (size_t)H2_STAGES * H2_STAGE_BYTES + EPI_WARPS * 32 * 128 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the address of the same shared-memory object in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm_e(void* smem_dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_e(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* cstage = smem + H2_STAGES * H2_STAGE_BYTES;                             // [EPI_WARPS][32 rows][128 B]
+    uint64_t* full = reinterpret_cast<uint64_t*>(cstage + EPI_WARPS * 32 * 128);
+    uint64_t* empty = full + H2_STAGES;
+    uint64_t* tfull = empty + H2_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_kb = (p.K + 63) / 64;
+    const int num_tiles = p.tiles_m * p.tiles_n;                                    // 256 x 256 tiles of the pair
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+        for (int s = 0; s < H2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                       // the same warp of both CTAs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int t = pair; t < num_tiles; t += npairs) {
+            const int m0 = (t / p.tiles_n) * 256 + (int)rank * 128, n0 = (t % p.tiles_n) * 256 + (int)rank * 128;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (leader) mbar_expect_tx_e(&full[stage], 2 * H2_STAGE_BYTES);      // the bytes of both CTAs land on the leader's barrier
+                const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+                uint8_t* sa = smem + stage * H2_STAGE_BYTES;
+                tma_load_2d_2sm_e(sa, &tmap_a, lbar, kb * 64, m0);
+                tma_load_2d_2sm_e(sa + H2_A_BYTES, &tmap_b, lbar, kb * 64, n0);
+                if (++stage == H2_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_h(256, 256);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * 256;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * H2_STAGE_BYTES);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + H2_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_f16_2sm_e(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_2sm_e(&empty[stage]);
+                    if (++stage == H2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2sm_e(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        uint8_t* stg = cstage + (warp - 2) * (32 * 128);
+        const int ch = lane & 7, rsub = lane >> 3;
+        __half* Cg = reinterpret_cast<__half*>(p.C);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = pair; t < num_tiles; t += npairs) {
+            const int m0 = (t / p.tiles_n) * 256 + (int)rank * 128, n0 = (t % p.tiles_n) * 256;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int row0 = m0 + q * 32;
+#pragma unroll 1
+            for (int i = 0; i < 2; ++i) {
+                const int c64 = half * 2 + i, col0 = n0 + c64 * 64;
+                if (row0 >= p.M) break;                     // warp-uniform
+                uint32_t pk[32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c64 * 64 + h * 32, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = col0 + h * 32 + 4 * j;
+                        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+                        if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+                        float v0 = fmaf(__uint_as_float(r[4 * j]), sc.x, sh.x), v1 = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+                        float v2 = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+                        v0 = fmaxf(v0, v0 * p.neg_slope); v1 = fmaxf(v1, v1 * p.neg_slope);
+                        v2 = fmaxf(v2, v2 * p.neg_slope); v3 = fmaxf(v3, v3 * p.neg_slope);
+                        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[h * 16 + 2 * j]) : "f"(v1), "f"(v0));
+                        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[h * 16 + 2 * j + 1]) : "f"(v3), "f"(v2));
+                    }
+                }
+                uint8_t* dst = stg + lane * 128;            // lane = row: 8 chunks of 16 B, chunk ^= row & 7
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rsub;
+                    const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                    if (row0 + rr < p.M) *reinterpret_cast<uint4*>(Cg + (size_t)(row0 + rr) * p.ldc + col0 + ch * 8) = v;
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {                               // the accumulator stage is free again: tell the leader's MMA warp
+                const uint32_t lbar = mapa_u32(smem_u32(&tempty[acc]), 0);
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                    // nobody leaves while the peer may still read its shared memory / barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+static int launch_h2(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
+    LPD_CUDA_CHECK(allow_smem(gemm_h2_kernel, H2_SMEM));
+    int dev = 0, sms = 0;
+    LPD_CUDA_CHECK(cudaGetDevice(&dev));
+    LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    p.tiles_m = ceil_div(p.M, 256);
+    p.tiles_n = p.N / 256;
+    const long long tiles = (long long)p.tiles_m * p.tiles_n;
+    const long long pairs = sms / 2;
+    const int grid = (int)(2 * (tiles < pairs ? tiles : pairs));
+    gemm_h2_kernel<<<grid, THREADS, H2_SMEM, st>>>(ta, tb, p);
+    LPD_LAUNCH_CHECK();
+    return LPD_OK;
+}
+
 __global__ void __launch_bounds__(256)
 f32_to_f16_kernel(const float* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, long long rows, int cols) {
     const long long total = rows * cols;
@@ -442,6 +645,9 @@ extern "C" int lpd_f32_to_f16(const float* x, long long ldx, void* y, long long 
     return LPD_OK;
 }
 
+// 1 (default): wide fp16-output layers on the CTA-pair kernel; 0: single-CTA kernel everywhere (LPD_GEMM_2CTA=0)
+static int g_gemm_2cta = [] { const char* e = getenv("LPD_GEMM_2CTA"); return (e && atoi(e) == 0) ? 0 : 1; }();
+
 extern "C" int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_half,
                             int M, int N, int K, const float* scale, const float* shift, int act, float slope, void* stream) {
     using namespace lpd;
@@ -466,6 +672,11 @@ extern "C" int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
     p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
+    if (out_half && (N % 256) == 0 && (ldc % 8) == 0 && g_gemm_2cta) {                // CTA-pair kernel (cta_group::2)
+        rc = tc::make_tmap_h(&tb, W, N, K, ldw, 128);                                  // each CTA loads 128 of the tile's 256 rows of W
+        if (rc != LPD_OK) return rc;
+        return tc::launch_h2(ta, tb, p, st);
+    }
     if (out_half) {
         if (BN == 64) return tc::launch<64, 8, false, __half, true>(ta, tb, p, st);
         if (BN == 128) return tc::launch<128, 6, false, __half, true>(ta, tb, p, st);

@@ -40,7 +40,7 @@ __device__ __forceinline__ int cell_coord(float v, float mn, float invh, int G) 
 __global__ void __launch_bounds__(GRID_BUILD_THREADS)
 knn_grid_build_kernel(const float* __restrict__ x, int N, int G, float4* __restrict__ sorted, int* __restrict__ sidx,
                       int* __restrict__ cell_start, GridHeader* __restrict__ hdr,
-                      int* __restrict__ perm_out, int* __restrict__ inv_out, float* __restrict__ xyz_out) {
+                      int* __restrict__ perm_out, int* __restrict__ inv_out, float* __restrict__ xyz_out, int identity_sidx) {
     __shared__ float red[7][32];
     __shared__ GridHeader h;
     __shared__ int counts[GRID_MAX_G * GRID_MAX_G * GRID_MAX_G + 1];
@@ -150,7 +150,7 @@ knn_grid_build_kernel(const float* __restrict__ x, int N, int G, float4* __restr
         if (valid) {
             const int pos = slot + rank;
             so[pos] = make_float4(a, c, d, __fmaf_rn(d, d, __fmaf_rn(c, c, __fmaf_rn(a, a, 0.f))));
-            si[pos] = i;
+            si[pos] = identity_sidx ? pos : i;             // identity: the grid is handed on as the grid of the RE-ORDERED cloud
             if (perm_out) perm_out[(size_t)b * N + pos] = i;
             if (inv_out) inv_out[(size_t)b * N + i] = pos;
             if (xyz_out) { float* o = xyz_out + ((size_t)b * N + pos) * 3; o[0] = a; o[1] = c; o[2] = d; }
@@ -361,7 +361,7 @@ struct GridBox { int x0, x1, y0, y1, z0, z1; };
 // not fit the buffer.  Not inlined: the kernel calls it from two places and has to fit the instruction cache.
 __device__ __noinline__ int gl_stage(int s, int myseg, int rowid, int cx, int G, const int* __restrict__ cs,
                                      const float4* __restrict__ so, const int* __restrict__ si, float* __restrict__ candf,
-                                     int* __restrict__ cidx, GridBox* box) {
+                                     int* __restrict__ cidx, int2* __restrict__ rng, GridBox* box) {
     const int lane = threadIdx.x & 31;
     const bool inseg = myseg == s;
     const int r = __shfl_sync(kFull, rowid, __ffs(__ballot_sync(kFull, inseg)) - 1);
@@ -372,24 +372,52 @@ __device__ __noinline__ int gl_stage(int s, int myseg, int rowid, int cx, int G,
     bx.y0 = max(ry - 1, 0); bx.y1 = min(ry + 1, G - 1);
     bx.z0 = max(rz - 1, 0); bx.z1 = min(rz + 1, G - 1);
     *box = bx;
-    int T = 0;
+    // the <= 9 ranges laid end to end on one flat index (lane = range): rng[r] = (start - first flat index, one past the last flat
+    // index), so that the copy below keeps four independent loads per lane in flight whatever the range lengths (walking the
+    // ranges one by one made the staging a chain of dependent L2 round trips: a third of the kernel's stall samples)
+    const int ny = bx.y1 - bx.y0 + 1, nr = ny * (bx.z1 - bx.z0 + 1);
+    int start = 0, len = 0;
+    if (lane < nr) {
+        const int row = ((bx.z0 + lane / ny) * G + bx.y0 + lane % ny) * G;
+        start = __ldg(cs + row + bx.x0);
+        len = __ldg(cs + row + bx.x1 + 1) - start;
+    }
+    int incl = len;
+#pragma unroll
+    for (int sft = 1; sft < 16; sft <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, sft);
+        if (lane >= sft) incl += up;
+    }
+    const int T = __shfl_sync(kFull, incl, 15);
     __syncwarp();                                          // the previous contents have been consumed
+    if (T > GL_CAND) return -1;
+    if (lane < nr) rng[lane] = make_int2(start - (incl - len), incl);
+    __syncwarp();
+    int rc = 0;
 #pragma unroll 1
-    for (int zz = bx.z0; zz <= bx.z1; ++zz)
-#pragma unroll 1
-        for (int yy = bx.y0; yy <= bx.y1; ++yy) {
-            const int rb = cs[(zz * G + yy) * G + bx.x0], len = cs[(zz * G + yy) * G + bx.x1 + 1] - rb;
-            if (T + len > GL_CAND) return -1;
-#pragma unroll 1
-            for (int p = lane; p < len; p += 32) {
-                const float4 c = __ldg(so + rb + p);
-                const int i = T + p;
-                float* d = candf + (i >> 1) * 8 + (i & 1);
-                d[0] = c.x; d[2] = c.y; d[4] = c.z; d[6] = -c.w;
-                cidx[i] = __ldg(si + rb + p);
+    for (int f0 = 0; f0 < T; f0 += 128) {
+        float4 c[4];
+        int id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int f = f0 + 32 * u + lane;
+            if (f < T) {
+                while (f >= rng[rc].y) ++rc;
+                const int p = f + rng[rc].x;
+                c[u] = __ldg(so + p);
+                id[u] = __ldg(si + p);
             }
-            T += len;
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = f0 + 32 * u + lane;
+            if (i < T) {
+                float* d = candf + (i >> 1) * 8 + (i & 1);
+                d[0] = c[u].x; d[2] = c[u].y; d[4] = c[u].z; d[6] = -c[u].w;
+                cidx[i] = id[u];
+            }
+        }
+    }
     const int Tp = (T + 63) & ~63;
 #pragma unroll 1
     for (int i = T + lane; i < Tp; i += 32) {
@@ -400,7 +428,7 @@ __device__ __noinline__ int gl_stage(int s, int myseg, int rowid, int cx, int G,
     return T;
 }
 
-__global__ void __launch_bounds__(GL_WARPS * 32)
+__global__ void __launch_bounds__(GL_WARPS * 32, 8)
 knn_grid_lockstep_kernel(const float4* __restrict__ sorted, const int* __restrict__ sidx, const int* __restrict__ cell_start,
                          const GridHeader* __restrict__ hdr, int N, int k, void* __restrict__ idx_out, int idx_i64,
                          int* __restrict__ rlist) {
@@ -411,6 +439,8 @@ knn_grid_lockstep_kernel(const float4* __restrict__ sorted, const int* __restric
     const ulonglong2* candp = reinterpret_cast<const ulonglong2*>(candf);
     int* cidx = reinterpret_cast<int*>(gsm + S::off_idx) + w * GL_CAND;
     uint32_t* maskbuf = reinterpret_cast<uint32_t*>(gsm + S::off_mask) + w * (GL_CAND / 32) * 32;   // [32-candidate block][lane]
+    __shared__ int2 rng_s[GL_WARPS][9];
+    int2* rng = rng_s[w];
     const int b = blockIdx.y;
     const int t0 = (blockIdx.x * GL_WARPS + w) * 32;
     if (t0 >= N) return;                                   // the whole warp is out of range
@@ -450,7 +480,7 @@ knn_grid_lockstep_kernel(const float4* __restrict__ sorted, const int* __restric
         for (int j = 0; j < 64; ++j) m[j] = -INFINITY;
 #pragma unroll 1
         for (int s = 0; s < nseg; ++s) {
-            const int T = gl_stage(s, myseg, rowid, cx, G, cs, so, si, candf, cidx, &box);
+            const int T = gl_stage(s, myseg, rowid, cx, G, cs, so, si, candf, cidx, rng, &box);
             Tlast = T;
             if (T < 0) { if (myseg == s) rescue = true; continue; }
             const f32x2 QW = (myseg == s) ? QWT : pack2(INFINITY);       // lanes of the other segments: every score -inf
@@ -467,8 +497,8 @@ knn_grid_lockstep_kernel(const float4* __restrict__ sorted, const int* __restric
             }
         }
         // ---- tau: a lower bound of the k-th largest of the 64 group maxima, by bisection on the value (a rolled loop of 64
-        //      compare-and-count steps: any tau with at least k group maxima at or above it is valid, and 12 halvings of the
-        //      range of the maxima leave it ~1/60 of a neighbour rank below the exact value) ----
+        //      compare-and-count steps: any tau with at least k group maxima at or above it is valid, and 9 halvings of the
+        //      range of the maxima leave it a small fraction of a neighbour rank below the exact value) ----
         float lo = INFINITY, hi = -INFINITY;
         int nfin = 0;
 #pragma unroll
@@ -481,7 +511,7 @@ knn_grid_lockstep_kernel(const float4* __restrict__ sorted, const int* __restric
         if (nfin < k) lo = -INFINITY;                      // fewer than k non-empty groups: everything is collected
         else {
 #pragma unroll 1
-            for (int it = 0; it < 12; ++it) {
+            for (int it = 0; it < 9; ++it) {
                 const float mid = 0.5f * lo + 0.5f * hi;
                 int c = 0;
 #pragma unroll
@@ -501,7 +531,7 @@ knn_grid_lockstep_kernel(const float4* __restrict__ sorted, const int* __restric
     float dmin2 = INFINITY;                                // squared distance to the nearest interior face of the lane's box
 #pragma unroll 1
     for (int s = 0; s < nseg; ++s) {
-        const int T = (nseg == 1) ? Tlast : gl_stage(s, myseg, rowid, cx, G, cs, so, si, candf, cidx, &box);   // a single segment is still staged
+        const int T = (nseg == 1) ? Tlast : gl_stage(s, myseg, rowid, cx, G, cs, so, si, candf, cidx, rng, &box);   // a single segment is still staged
         if (T < 0) continue;
         const bool inseg = myseg == s;
         const float tq = inseg ? tau : INFINITY;           // lanes of the other segments collect nothing (a score is never +inf)
@@ -809,9 +839,9 @@ extern "C" size_t lpd_knn_xyz_workspace_bytes(int B, int N) {
            + ((size_t)B * N + 4) * sizeof(int);                // + the rescue list of the lock-step search
 }
 
-extern "C" int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes,
-                           void* stream) {
-    LPD_REQUIRE(x && idx && workspace);
+static int knn_xyz_impl(const float* x, int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    LPD_REQUIRE(idx && workspace);
     LPD_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && k >= 1 && k <= 32 && k <= N);
     LPD_REQUIRE(((uintptr_t)workspace & 15) == 0);
     if (workspace_bytes < lpd_knn_xyz_workspace_bytes(B, N)) return LPD_EWORKSPACE;
@@ -824,8 +854,10 @@ extern "C" int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int i
     hdr = reinterpret_cast<GridHeader*>((reinterpret_cast<uintptr_t>(hdr) + 15) & ~(uintptr_t)15);
     const int G = grid_cells_per_axis(N);
     cudaStream_t st = as_stream(stream);
-    knn_grid_build_kernel<<<B, GRID_BUILD_THREADS, 0, st>>>(x, N, G, sorted, sidx, cell_start, hdr, nullptr, nullptr, nullptr);
-    LPD_LAUNCH_CHECK();
+    if (x) {                                               // x == nullptr: the workspace already holds the grid (lpd_knn_xyz_ordered)
+        knn_grid_build_kernel<<<B, GRID_BUILD_THREADS, 0, st>>>(x, N, G, sorted, sidx, cell_start, hdr, nullptr, nullptr, nullptr, 0);
+        LPD_LAUNCH_CHECK();
+    }
     dim3 grid(ceil_div(N, GRID_Q_THREADS), B);
     const int gs = (k + 3) / 4;
     // lock-step search first; the thread-per-query kernel then only finishes the queries on its rescue list
@@ -857,12 +889,24 @@ extern "C" int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int i
     return LPD_OK;
 }
 
+extern "C" int lpd_knn_xyz(const float* x, int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    LPD_REQUIRE(x);
+    return knn_xyz_impl(x, B, N, k, idx, idx_i64, workspace, workspace_bytes, stream);
+}
+
+// kNN of the cloud lpd_cell_order_grid wrote to xyz_sorted, on the grid that call left in `workspace`: a cloud in cell order is
+// its own counting sort (same bounding box, same cells, stable order), so the second build is skipped.
+extern "C" int lpd_knn_xyz_ordered(int B, int N, int k, void* idx, int idx_i64, void* workspace, size_t workspace_bytes, void* stream) {
+    return knn_xyz_impl(nullptr, B, N, k, idx, idx_i64, workspace, workspace_bytes, stream);
+}
+
 // Spatial (grid-cell) order of every cloud: perm[b][t] = original index of the t-th point in cell order (stable inside a
 // cell), inv = its inverse, xyz_sorted = the coordinates in that order.  The hot path is permutation-equivariant per point
 // and NetVLAD sums over the points, so the host modules may run a cloud in this order: neighbours in space become
 // neighbours in memory (gather locality) and the kNN candidate lists converge after the first few tiles.
-extern "C" int lpd_cell_order(const float* x, int B, int N, int32_t* perm, int32_t* inv, float* xyz_sorted,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+static int cell_order_impl(const float* x, int B, int N, int32_t* perm, int32_t* inv, float* xyz_sorted,
+                           void* workspace, size_t workspace_bytes, void* stream, int identity) {
     LPD_REQUIRE(x && perm && workspace && B >= 1 && B <= 65535 && N >= 1);
     LPD_REQUIRE(((uintptr_t)workspace & 15) == 0);
     if (workspace_bytes < lpd_knn_xyz_workspace_bytes(B, N)) return LPD_EWORKSPACE;
@@ -873,7 +917,18 @@ extern "C" int lpd_cell_order(const float* x, int B, int N, int32_t* perm, int32
     GridHeader* hdr = reinterpret_cast<GridHeader*>(cell_start + (size_t)B * cells1);
     hdr = reinterpret_cast<GridHeader*>((reinterpret_cast<uintptr_t>(hdr) + 15) & ~(uintptr_t)15);
     knn_grid_build_kernel<<<B, GRID_BUILD_THREADS, 0, as_stream(stream)>>>(x, N, grid_cells_per_axis(N), sorted, sidx, cell_start, hdr,
-                                                                        perm, inv, xyz_sorted);
+                                                                        perm, inv, xyz_sorted, identity);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
+}
+
+extern "C" int lpd_cell_order(const float* x, int B, int N, int32_t* perm, int32_t* inv, float* xyz_sorted,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    return cell_order_impl(x, B, N, perm, inv, xyz_sorted, workspace, workspace_bytes, stream, 0);
+}
+
+extern "C" int lpd_cell_order_grid(const float* x, int B, int N, int32_t* perm, int32_t* inv, float* xyz_sorted,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    LPD_REQUIRE(xyz_sorted);
+    return cell_order_impl(x, B, N, perm, inv, xyz_sorted, workspace, workspace_bytes, stream, 1);
 }

@@ -72,20 +72,6 @@ split_kernel(const float* __restrict__ x, int n, int n_pad, int D, int is_db, fl
     }
 }
 
-// insert candidate (cv, cj) into the warp-distributed ascending list (lane l = l-th smallest; ties -> lower index)
-__device__ __forceinline__ void list_insert(double& lv, int& li, double cv, int cj, int k, int lane) {
-    const bool better = (lv < cv) || (lv == cv && li < cj);
-    const int pos = __popc(__ballot_sync(kFull, better));
-    if (pos < k) {
-        const double upv = __shfl_up_sync(kFull, lv, 1);
-        const int upi = __shfl_up_sync(kFull, li, 1);
-        if (lane < k) {
-            if (lane > pos) { lv = upv; li = upi; }
-            else if (lane == pos) { lv = cv; li = cj; }
-        }
-    }
-}
-
 // one warp per (query, segment)
 __global__ void __launch_bounds__(256)
 select_refine_kernel(const float* __restrict__ A, int lda, const float* __restrict__ db, const float* __restrict__ q, int Nq, int D,
@@ -99,6 +85,9 @@ select_refine_kernel(const float* __restrict__ A, int lda, const float* __restri
     const int s = (int)(unit / Nq), i = (int)(unit % Nq);         // consecutive warps: consecutive queries of one segment
     const int r0 = seg_off[s], r1 = seg_off[s + 1];
     float* qs = qsm + warp * D;
+    int* cjs = reinterpret_cast<int*>(qsm + 8 * D) + warp * CHUNK;                    // compacted candidate rows of a chunk
+    double* mvs = reinterpret_cast<double*>(reinterpret_cast<int*>(qsm + 8 * D) + 8 * CHUNK) + warp * 32;   // merge buffer
+    int* mis = reinterpret_cast<int*>(reinterpret_cast<double*>(reinterpret_cast<int*>(qsm + 8 * D) + 8 * CHUNK) + 8 * 32) + warp * 32;
     for (int d = lane; d < D; d += 32) qs[d] = __ldg(q + (size_t)i * D + d);
     __syncwarp();
     const float qn = sqrtf(qnorm2[i]) * 1.0000002f, xm = __uint_as_float(*dmax_bits);
@@ -142,17 +131,26 @@ select_refine_kernel(const float* __restrict__ A, int lda, const float* __restri
             const float cap = (float)(kth - (double)qnorm2[i]) + 2.f * eps + 1e-6f * fabsf((float)kth);
             thr = fminf(thr, cap);
         }
-#pragma unroll 1
+        // ---- the candidates of this chunk, compacted (they are scattered over the 32 x 32 positions of the chunk: re-scoring them
+        //      where they lie ran the 256-step fp64 chain ~20 times per warp with one or two live lanes: 0.75 ms of the 1.0 ms pass) ----
+        int ncand = 0;
+#pragma unroll
         for (int t = 0; t < CHUNK / 32; ++t) {
             const bool pass = v[t] <= thr;
-            if (!__any_sync(kFull, pass)) continue;
+            const unsigned bal = __ballot_sync(kFull, pass);
+            if (pass) cjs[ncand + __popc(bal & ((1u << lane) - 1u))] = c0 + t * 32 + lane;
+            ncand += __popc(bal);
+        }
+        __syncwarp();
+        for (int base = 0; base < ncand; base += 32) {
             // exact distance: one candidate per lane, d ascending, fma — the arithmetic of lpd_retrieval_topk
-            const int j = c0 + t * 32 + lane;
+            const int j = base + lane < ncand ? cjs[base + lane] : INT_MAX;
             double acc = INFINITY;
-            if (pass) {
+            if (j != INT_MAX) {
                 acc = 0.0;
                 const float4* row = reinterpret_cast<const float4*>(db + (size_t)j * D);
                 if ((D & 3) == 0) {
+#pragma unroll 4
                     for (int d4 = 0; d4 < D / 4; ++d4) {
                         const float4 x = __ldg(row + d4);
                         const float4 qq = *reinterpret_cast<const float4*>(qs + 4 * d4);
@@ -168,15 +166,26 @@ select_refine_kernel(const float* __restrict__ A, int lda, const float* __restri
                     }
                 }
             }
-            unsigned mask = __ballot_sync(kFull, pass);
-            while (mask) {
-                const int src = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const double cv = __shfl_sync(kFull, acc, src);
-                const int cj = __shfl_sync(kFull, j, src);
-                list_insert(lv, li, cv, cj, k, lane);
+            // merge the <= 32 new entries into the running ascending list (lane l = l-th smallest; ties -> lower index) by
+            // counting: an entry's new position = the number of entries of both sets that come before it
+            int rank_new = 0, rank_old = lane;
+#pragma unroll 4
+            for (int src = 0; src < 32; ++src) {
+                const double ov = __shfl_sync(kFull, lv, src), nv = __shfl_sync(kFull, acc, src);
+                const int oi = __shfl_sync(kFull, li, src), ni = __shfl_sync(kFull, j, src);
+                rank_new += ((ov < acc) || (ov == acc && oi < j)) + ((nv < acc) || (nv == acc && ni < j));
+                rank_old += (nv < lv) || (nv == lv && ni < li);
             }
+            __syncwarp();
+            mvs[lane] = INFINITY; mis[lane] = INT_MAX;
+            __syncwarp();
+            if (li != INT_MAX && rank_old < 32) { mvs[rank_old] = lv; mis[rank_old] = li; }
+            if (j != INT_MAX && rank_new < 32) { mvs[rank_new] = acc; mis[rank_new] = j; }
+            __syncwarp();
+            lv = lane < k ? mvs[lane] : (double)INFINITY;
+            li = lane < k ? mis[lane] : INT_MAX;
         }
+        __syncwarp();
     }
     if (lane < k) {
         const size_t o = ((size_t)s * Nq + i) * k + lane;
@@ -283,7 +292,9 @@ extern "C" int lpd_retrieval_tc(const float* db, int Ndb, const float* q, int Nq
     int rc = lpd_gemm_tf32_ex(qs, 3 * D, dbs, 3 * D, A, L.ndb_pad, Nq, L.ndb_pad, 3 * D, 1, 0, fill, dn, LPD_ACT_NONE, 0.f, stream);
     if (rc != LPD_OK) return rc;
     const long long units = (long long)Nq * S;
-    const size_t smem = (size_t)8 * D * sizeof(float);
+    const size_t smem = (size_t)8 * D * sizeof(float) + (size_t)8 * rtc::CHUNK * sizeof(int) + 8 * 32 * (sizeof(double) + sizeof(int));
+    LPD_REQUIRE((D % 2) == 0 && smem <= 200 * 1024);
+    LPD_CUDA_CHECK(allow_smem(rtc::select_refine_kernel, smem));
     rtc::select_refine_kernel<<<(unsigned)ceil_div_ll(units, 8), 256, smem, st>>>(A, L.ndb_pad, db, q, Nq, D, k, seg_off, S, qn, xmax,
                                                                                  global_idx, idx_offset, idx, dist);
     LPD_LAUNCH_CHECK();

@@ -143,6 +143,10 @@ def knn(x_pm: torch.Tensor, k: int, int64: bool = False, diag: dict | None = Non
             off = lib.lpd_knn_tc_flags_offset(B, N, Cc, k) // 4
             diag["flagged_tiles"] = int((ws.view(torch.int32)[off: off + B * ((N + 63) // 64)] != 0).sum().item())
             diag["tiles"] = B * ((N + 63) // 64)
+    elif KNN_GRID and Cc == 3 and N >= 64 and _grid_of(x_pm) is not None:
+        # the cloud came out of cell_order(): its search grid is already in that call's workspace
+        ws = _grid_of(x_pm)
+        _call(f"lpd_knn_xyz[k={k}]", 2, lib.lpd_knn_xyz_ordered, B, N, k, idx.data_ptr(), int(int64), ws.data_ptr(), ws.numel() * 4, _stream())
     elif KNN_GRID and Cc == 3 and N >= 64:
         nbytes = lib.lpd_knn_xyz_workspace_bytes(B, N)
         ws = torch.empty((nbytes + 3) // 4, device=x_pm.device, dtype=torch.float32)
@@ -158,8 +162,22 @@ def knn(x_pm: torch.Tensor, k: int, int64: bool = False, diag: dict | None = Non
 SPATIAL_ORDER = True
 
 
+# one-entry cache: the re-ordered cloud of the last cell_order() call and the workspace holding its search grid.  The cache keeps
+# both tensors alive, so the data pointer identifies the cloud; _version catches in-place edits.
+_grid_cache = None
+
+
+def _grid_of(x_pm: torch.Tensor):
+    c = _grid_cache
+    if (c is not None and x_pm.data_ptr() == c[0].data_ptr() and tuple(x_pm.shape) == tuple(c[0].shape) and c[0]._version == c[2]
+            and x_pm.device == c[0].device):
+        return c[1]
+    return None
+
+
 def cell_order(xyz: torch.Tensor, want_inv: bool = False):
-    """xyz [B, N, 3] -> (perm int32 [B, N], inv int32 [B, N] or None, xyz_sorted [B, N, 3])"""
+    """xyz [B, N, 3] -> (perm int32 [B, N], inv int32 [B, N] or None, xyz_sorted [B, N, 3]).  knn(xyz_sorted, k) reuses the grid this
+    call built (lpd_cell_order_grid / lpd_knn_xyz_ordered)."""
     lib = _lib.load()
     xyz = _f32(xyz, "xyz").contiguous()
     B, N, _ = xyz.shape
@@ -168,8 +186,10 @@ def cell_order(xyz: torch.Tensor, want_inv: bool = False):
     out = torch.empty_like(xyz)
     nbytes = lib.lpd_knn_xyz_workspace_bytes(B, N)
     ws = torch.empty((nbytes + 3) // 4, device=xyz.device, dtype=torch.float32)
-    _call("lpd_cell_order", 1, lib.lpd_cell_order, xyz.data_ptr(), B, N, perm.data_ptr(), _p(inv), out.data_ptr(), ws.data_ptr(),
+    _call("lpd_cell_order", 1, lib.lpd_cell_order_grid, xyz.data_ptr(), B, N, perm.data_ptr(), _p(inv), out.data_ptr(), ws.data_ptr(),
           ws.numel() * 4, _stream())
+    global _grid_cache
+    _grid_cache = (out, ws, out._version)
     return perm, inv, out
 
 

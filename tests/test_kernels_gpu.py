@@ -79,6 +79,24 @@ def test_knn_xyz_grid_is_bit_exact_on_adversarial_clouds(cuda, kind, k):
         ops.KNN_GRID = prev
 
 
+def test_knn_xyz_on_the_grid_left_by_cell_order(cuda):
+    """knn(xyz_sorted) right after cell_order() reuses that call's grid (lpd_cell_order_grid + lpd_knn_xyz_ordered): same lists as the
+    brute-force kernel on the re-ordered cloud; an edited or foreign cloud takes the ordinary path"""
+    for B, N, k in ((3, 1000, 20), (2, 4096, 20), (2, 700, 9), (1, 2048, 32)):
+        x = synth.clouds(B, N, seed=5 + N)[:, 0].contiguous().cuda()
+        perm, inv, xs = ops.cell_order(x, want_inv=True)
+        assert ops._grid_of(xs) is not None
+        got = ops.knn(xs, k).cpu().numpy()
+        assert np.array_equal(got, knn_canonical(xs.cpu().numpy(), k))
+        assert np.array_equal(xs.cpu().numpy(), np.take_along_axis(x.cpu().numpy(), perm.cpu().numpy()[..., None].astype(np.int64), 1))
+        other = xs.clone()
+        assert ops._grid_of(other) is None
+        assert np.array_equal(ops.knn(other, k).cpu().numpy(), got)
+        xs.mul_(1.5)                                                        # edited in place: the cached grid no longer applies
+        assert ops._grid_of(xs) is None
+        assert np.array_equal(ops.knn(xs, k).cpu().numpy(), knn_canonical(xs.cpu().numpy(), k))
+
+
 def test_knn_matches_reference_golden_sets(cuda, golden):
     """against the reference's own torch knn() output (tie-aware: sets may differ only on near-ties)"""
     from _helpers import assert_knn_equivalent
@@ -144,7 +162,8 @@ def test_bn_fold_transpose_colmax_splitk(cuda):
 
 
 @pytest.mark.parametrize("M,N,K,lda,out_half", [(300, 64, 1024, 1024, False), (1000, 1024, 512, 512, True), (129, 512, 128, 256, False),
-                                                (4096, 256, 64, 64, True), (128, 68, 72, 80, False)])
+                                                (4096, 256, 64, 64, True), (128, 68, 72, 80, False),
+                                                (70000, 512, 128, 128, True), (257, 256, 200, 208, True), (40000, 1024, 512, 512, True)])
 def test_gemm_f16_operands(cuda, M, N, K, lda, out_half):
     """lpd_gemm_f16: fp16 operands, fp32 accumulation on tcgen05 kind::f16, fused affine + LeakyReLU epilogue, fp32 or fp16
     output — against float64 on the SAME fp16-rounded operands (so only accumulation order and the output rounding differ)"""
