@@ -406,6 +406,18 @@ __device__ __forceinline__ void tc_commit_2sm_e(uint64_t* bar) {      // arrives
         ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tc_mma_tf32_2sm_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// TIN = __half: fp16 operands (kind::f16, 64 K elements per 128-byte row); TIN = float: fp32 operands consumed as TF32 (32 per row)
+template <typename TIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -420,7 +432,9 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int num_kb = (p.K + 63) / 64;
+    constexpr bool HALF = sizeof(TIN) == 2;
+    constexpr int BKE = HALF ? 64 : 32;                                             // K elements per ring slot
+    const int num_kb = (p.K + BKE - 1) / BKE;
     const int num_tiles = p.tiles_m * p.tiles_n;                                    // 256 x 256 tiles of the pair
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
@@ -449,14 +463,14 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (leader) mbar_expect_tx_e(&full[stage], 2 * H2_STAGE_BYTES);      // the bytes of both CTAs land on the leader's barrier
                 const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
                 uint8_t* sa = smem + stage * H2_STAGE_BYTES;
-                tma_load_2d_2sm_e(sa, &tmap_a, lbar, kb * 64, m0);
-                tma_load_2d_2sm_e(sa + H2_A_BYTES, &tmap_b, lbar, kb * 64, n0);
+                tma_load_2d_2sm_e(sa, &tmap_a, lbar, kb * BKE, m0);
+                tma_load_2d_2sm_e(sa + H2_A_BYTES, &tmap_b, lbar, kb * BKE, n0);
                 if (++stage == H2_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (leader) {
-            constexpr uint32_t idesc = make_idesc_h(256, 256);
+            constexpr uint32_t idesc = HALF ? make_idesc_h(256, 256) : make_idesc(256, 256);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = pair; t < num_tiles; t += npairs) {
@@ -469,7 +483,10 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint32_t sa = smem_u32(smem + stage * H2_STAGE_BYTES);
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + H2_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tc_mma_f16_2sm_e(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {              // 32 bytes of K per MMA: 16 fp16 or 8 tf32 elements
+                        if (HALF) tc_mma_f16_2sm_e(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        else tc_mma_tf32_2sm_e(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     tc_commit_2sm_e(&empty[stage]);
                     if (++stage == H2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -541,8 +558,9 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+template <typename TIN>
 static int launch_h2(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
-    LPD_CUDA_CHECK(allow_smem(gemm_h2_kernel, H2_SMEM));
+    LPD_CUDA_CHECK(allow_smem(gemm_h2_kernel<TIN>, H2_SMEM));
     int dev = 0, sms = 0;
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -551,7 +569,7 @@ static int launch_h2(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cud
     const long long tiles = (long long)p.tiles_m * p.tiles_n;
     const long long pairs = sms / 2;
     const int grid = (int)(2 * (tiles < pairs ? tiles : pairs));
-    gemm_h2_kernel<<<grid, THREADS, H2_SMEM, st>>>(ta, tb, p);
+    gemm_h2_kernel<TIN><<<grid, THREADS, H2_SMEM, st>>>(ta, tb, p);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }
@@ -675,7 +693,7 @@ extern "C" int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void
     if (out_half && (N % 256) == 0 && (ldc % 8) == 0 && g_gemm_2cta) {                // CTA-pair kernel (cta_group::2)
         rc = tc::make_tmap_h(&tb, W, N, K, ldw, 128);                                  // each CTA loads 128 of the tile's 256 rows of W
         if (rc != LPD_OK) return rc;
-        return tc::launch_h2(ta, tb, p, st);
+        return tc::launch_h2<__half>(ta, tb, p, st);
     }
     if (out_half) {
         if (BN == 64) return tc::launch<64, 8, false, __half, true>(ta, tb, p, st);
@@ -771,6 +789,11 @@ extern "C" int lpd_gemm_tf32_out16(const float* A, int lda, const float* B, int 
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
     p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
+    if ((N % 256) == 0 && (ldc % 8) == 0 && g_gemm_2cta) {                             // CTA-pair kernel (cta_group::2)
+        rc = tc::make_tmap(&tb, B, N, K, ldb, 128);
+        if (rc != LPD_OK) return rc;
+        return tc::launch_h2<float>(ta, tb, p, st);
+    }
     if (BN == 64) return tc::launch<64, 8, false, float, true>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6, false, float, true>(ta, tb, p, st);
     return tc::launch<256, 4, false, float, true>(ta, tb, p, st);

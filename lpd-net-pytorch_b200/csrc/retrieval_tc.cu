@@ -84,11 +84,11 @@ select_refine_kernel(const float* __restrict__ A, int lda, const float* __restri
     if (unit >= (long long)Nq * S) return;
     const int s = (int)(unit / Nq), i = (int)(unit % Nq);         // consecutive warps: consecutive queries of one segment
     const int r0 = seg_off[s], r1 = seg_off[s + 1];
-    float* qs = qsm + warp * D;
-    int* cjs = reinterpret_cast<int*>(qsm + 8 * D) + warp * CHUNK;                    // compacted candidate rows of a chunk
-    double* mvs = reinterpret_cast<double*>(reinterpret_cast<int*>(qsm + 8 * D) + 8 * CHUNK) + warp * 32;   // merge buffer
-    int* mis = reinterpret_cast<int*>(reinterpret_cast<double*>(reinterpret_cast<int*>(qsm + 8 * D) + 8 * CHUNK) + 8 * 32) + warp * 32;
-    for (int d = lane; d < D; d += 32) qs[d] = __ldg(q + (size_t)i * D + d);
+    double* qs = reinterpret_cast<double*>(qsm) + warp * D;       // the query row, converted once
+    int* cjs = reinterpret_cast<int*>(qsm + 16 * D) + warp * CHUNK;                   // compacted candidate rows of a chunk
+    double* mvs = reinterpret_cast<double*>(reinterpret_cast<int*>(qsm + 16 * D) + 8 * CHUNK) + warp * 32;   // merge buffer
+    int* mis = reinterpret_cast<int*>(reinterpret_cast<double*>(reinterpret_cast<int*>(qsm + 16 * D) + 8 * CHUNK) + 8 * 32) + warp * 32;
+    for (int d = lane; d < D; d += 32) qs[d] = (double)__ldg(q + (size_t)i * D + d);
     __syncwarp();
     const float qn = sqrtf(qnorm2[i]) * 1.0000002f, xm = __uint_as_float(*dmax_bits);
     const float eps = 2.f * (qn * xm * 4.8828125e-4f) + 9.5367431640625e-7f * (xm * xm + 2.f * qn * xm);
@@ -107,13 +107,24 @@ select_refine_kernel(const float* __restrict__ A, int lda, const float* __restri
             key[t] = fkey(v[t]);
         }
         const int kk = min(k, len);
-        // smallest T with count(key <= T) >= kk
-        unsigned lo = 0u, hi = 0xffffffffu;
-        {   // narrow the range to [min key, max finite key] first: saves most of the 32 bisection steps' worth of nothing
+        // a threshold T with count(key <= T) >= kk, as tight as cheap: (1) the kk-th smallest of the 32 per-lane minima is an upper
+        // bound of the kk-th smallest score (kk distinct scores reach it); (2) bisection on the order-preserving integer image between
+        // the smallest score and that bound, stopped as soon as the count lands in [kk, kk + 3] (any such T keeps the exact top-k in
+        // the candidate set; three extra candidates cost less than the ~20 further halvings down to a single key)
+        unsigned lo, hi;
+        {
             unsigned mn = 0xffffffffu;
 #pragma unroll
             for (int t = 0; t < CHUNK / 32; ++t) mn = min(mn, key[t]);
             lo = __reduce_min_sync(kFull, mn);
+            int rank = 0;
+#pragma unroll 8
+            for (int src = 0; src < 32; ++src) {
+                const unsigned o = __shfl_sync(kFull, mn, src);
+                rank += (o < mn) || (o == mn && src < lane);
+            }
+            const unsigned pick = __ballot_sync(kFull, rank == min(kk, 32) - 1);
+            hi = __shfl_sync(kFull, mn, __ffs(pick) - 1);
         }
         while (lo < hi) {
             const unsigned mid = lo + ((hi - lo) >> 1);
@@ -121,8 +132,9 @@ select_refine_kernel(const float* __restrict__ A, int lda, const float* __restri
 #pragma unroll
             for (int t = 0; t < CHUNK / 32; ++t) c += key[t] <= mid;
             c = __reduce_add_sync(kFull, c);
-            if (c >= kk) hi = mid; else lo = mid + 1;
+            if (c >= kk) { hi = mid; if (c <= kk + 3) break; } else lo = mid + 1;
         }
+        lo = hi;
         float T = fkey_inv(lo);
         // later chunks of a long segment: nothing worse than the running k-th exact distance can enter the list
         const double kth = __shfl_sync(kFull, lv, k - 1);
@@ -153,15 +165,15 @@ select_refine_kernel(const float* __restrict__ A, int lda, const float* __restri
 #pragma unroll 4
                     for (int d4 = 0; d4 < D / 4; ++d4) {
                         const float4 x = __ldg(row + d4);
-                        const float4 qq = *reinterpret_cast<const float4*>(qs + 4 * d4);
-                        double tt = (double)qq.x - (double)x.x; acc = fma(tt, tt, acc);
-                        tt = (double)qq.y - (double)x.y; acc = fma(tt, tt, acc);
-                        tt = (double)qq.z - (double)x.z; acc = fma(tt, tt, acc);
-                        tt = (double)qq.w - (double)x.w; acc = fma(tt, tt, acc);
+                        const double2 qa = *reinterpret_cast<const double2*>(qs + 4 * d4), qb = *reinterpret_cast<const double2*>(qs + 4 * d4 + 2);
+                        double tt = qa.x - (double)x.x; acc = fma(tt, tt, acc);
+                        tt = qa.y - (double)x.y; acc = fma(tt, tt, acc);
+                        tt = qb.x - (double)x.z; acc = fma(tt, tt, acc);
+                        tt = qb.y - (double)x.w; acc = fma(tt, tt, acc);
                     }
                 } else {
                     for (int d = 0; d < D; ++d) {
-                        const double tt = (double)qs[d] - (double)__ldg(db + (size_t)j * D + d);
+                        const double tt = qs[d] - (double)__ldg(db + (size_t)j * D + d);
                         acc = fma(tt, tt, acc);
                     }
                 }
@@ -292,7 +304,7 @@ extern "C" int lpd_retrieval_tc(const float* db, int Ndb, const float* q, int Nq
     int rc = lpd_gemm_tf32_ex(qs, 3 * D, dbs, 3 * D, A, L.ndb_pad, Nq, L.ndb_pad, 3 * D, 1, 0, fill, dn, LPD_ACT_NONE, 0.f, stream);
     if (rc != LPD_OK) return rc;
     const long long units = (long long)Nq * S;
-    const size_t smem = (size_t)8 * D * sizeof(float) + (size_t)8 * rtc::CHUNK * sizeof(int) + 8 * 32 * (sizeof(double) + sizeof(int));
+    const size_t smem = (size_t)8 * D * sizeof(double) + (size_t)8 * rtc::CHUNK * sizeof(int) + 8 * 32 * (sizeof(double) + sizeof(int));
     LPD_REQUIRE((D % 2) == 0 && smem <= 200 * 1024);
     LPD_CUDA_CHECK(allow_smem(rtc::select_refine_kernel, smem));
     rtc::select_refine_kernel<<<(unsigned)ceil_div_ll(units, 8), 256, smem, st>>>(A, L.ndb_pad, db, q, Nq, D, k, seg_off, S, qn, xmax,

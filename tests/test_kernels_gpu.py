@@ -183,6 +183,22 @@ def test_gemm_f16_operands(cuda, M, N, K, lda, out_half):
     assert np.array_equal(ops.to_f16(dev(x32)).cpu().numpy(), x32.astype(np.float16))
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 64), (70000, 256, 64), (300, 512, 100), (513, 128, 64)])
+def test_gemm_tf32_with_fp16_output(cuda, M, N, K):
+    """lpd_gemm_tf32_out16 (fp32 operands as TF32, fp16 output; N % 256 == 0 runs on the CTA-pair kernel) against float64 on the
+    TF32-truncated operands"""
+    r = rng(M + N + K)
+    A = r.standard_normal((M, K)).astype(np.float32)
+    W = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    sc, sh = r.standard_normal(N).astype(np.float32), r.standard_normal(N).astype(np.float32)
+    trunc = lambda x: (x.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+    ref = trunc(A).astype(np.float64) @ trunc(W).astype(np.float64).T * sc + sh
+    ref = np.maximum(ref, 0.0)
+    got = ops.gemm_tf32_out16(dev(A), dev(W), M=M, N=N, K=K, scale=dev(sc), shift=dev(sh), act=ops.ACT_RELU)
+    assert got.dtype == torch.float16 and tuple(got.shape) == (M, N)
+    assert np.abs(got.float().cpu().numpy() - ref).max() <= 2.0 ** -10 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("M,N,K,batch", [(1024, 64, 4096, 3), (128, 64, 64, 1), (200, 72, 1000, 1), (1024, 64, 16384, 2)])
 def test_gemm_f16_tn_contraction_over_rows(cuda, M, N, K, batch):
     """lpd_gemm_f16_tn: out[z] = A[z]^T . B[z] over the rows of two fp16 point-major maps (the NetVLAD aggregate in f16 mode)"""
