@@ -1047,9 +1047,13 @@ template <int CAP>
 static int knn2_refine_launch(const float* x, const float* xxpad, const int* cnt, const int* cand, int B, int N, int Npad, int k,
                               void* idx, int idx_i64, int* flags, int* list, cudaStream_t st) {
     if (g_refine_tma) {
-        if (g_refine_warps == 4) return knn2_refine_tma_launch<CAP, 4>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
-        if (g_refine_warps == 11) return knn2_refine_tma_launch<CAP, 11>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
-        return knn2_refine_tma_launch<CAP, 22>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
+        if constexpr (CAP > 64) {                          // (the per-warp key / id buffers grow with CAP: 16 warps fit)
+            return knn2_refine_tma_launch<CAP, 16>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
+        } else {
+            if (g_refine_warps == 4) return knn2_refine_tma_launch<CAP, 4>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
+            if (g_refine_warps == 11) return knn2_refine_tma_launch<CAP, 11>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
+            return knn2_refine_tma_launch<CAP, 22>(x, xxpad, cnt, cand, B, N, Npad, k, idx, idx_i64, flags, list, st);
+        }
     }
     const size_t smem = RefineSmem<CAP>::total;
     LPD_CUDA_CHECK(allow_smem(knn2_refine_kernel<CAP>, smem));
@@ -1087,7 +1091,7 @@ struct Knn2Ws {
     int npad, cap;
     Knn2Ws(int B, int N, int k) {
         npad = (N + 255) / 256 * 256;
-        cap = (k <= 24 && g_cap_small == 40) ? 40 : 64;
+        cap = k > 24 ? 128 : (g_cap_small == 40 ? 40 : 64);   // k > 24 (the per-candidate bound: ~45 candidates per row): 128 slots per half
         size_t o = 0;
         off_xx = o; o = align_up2(o + (size_t)B * npad * 4, 256);
         off_nrm = o; o = align_up2(o + (size_t)B * npad * 4, 256);
@@ -1154,16 +1158,17 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     P.cand = reinterpret_cast<int*>(ws + W.off_cand);
     P.B = B; P.N = N; P.Npad = W.npad; P.k = k;
     P.qtiles = ceil_div(N, mt == 2 ? 256 : 128); P.ctiles = ceil_div(N, K2_C);
-    // k <= 24: 40 slots per (row, half), uniform error bound; k <= 32: 64 slots, per-candidate bound
+    // k <= 24: 64 (or 40) slots per (row, half), uniform error bound; k <= 32: 128 slots, per-candidate bound
     if (mt == 3) {          // 128 rows per item, query tile in tensor memory (TS-mode MMA)
         rc = (W.cap == 40) ? knn2_launch<1, 40, false, true>(ta, tb, P, st)
-                           : (k <= 24 ? knn2_launch<1, 64, false, true>(ta, tb, P, st) : knn2_launch<1, 64, true, true>(ta, tb, P, st));
+                           : (k <= 24 ? knn2_launch<1, 64, false, true>(ta, tb, P, st) : knn2_launch<1, 128, true, true>(ta, tb, P, st));
     } else if (W.cap == 40) rc = (mt == 2) ? knn2_launch<2, 40, false>(ta, tb, P, st) : knn2_launch<1, 40, false>(ta, tb, P, st);
     else if (k <= 24) rc = (mt == 2) ? knn2_launch<2, 64, false>(ta, tb, P, st) : knn2_launch<1, 64, false>(ta, tb, P, st);
-    else             rc = (mt == 2) ? knn2_launch<2, 64, true>(ta, tb, P, st) : knn2_launch<1, 64, true>(ta, tb, P, st);
+    else             rc = (mt == 2) ? knn2_launch<2, 128, true>(ta, tb, P, st) : knn2_launch<1, 128, true>(ta, tb, P, st);
     if (rc != LPD_OK) return rc;
     rc = (W.cap == 40) ? knn2_refine_launch<40>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, list, st)
-                       : knn2_refine_launch<64>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, list, st);
+         : (W.cap == 64 ? knn2_refine_launch<64>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, list, st)
+                        : knn2_refine_launch<128>(x, xxpad, P.cnt, P.cand, B, N, W.npad, k, idx, idx_i64, flags, list, st));
     if (rc != LPD_OK) return rc;
     return knn_simt64_list(x, B, N, k, idx, idx_i64, list, st);       // exact recompute of the flagged 64-row tiles only
 }
