@@ -211,6 +211,10 @@ int lpd_edge_gather_max_f16(const void* p, int ldp, const void* q, int ldq, cons
 int lpd_edgeconv_dg20_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N,
                           const void* w2, const float* s2, const float* t2, int act, float slope,
                           void* x1, int ld1, void* x2, int ld2, void* stream);
+/* the same kernel for k == 32 (idx [B][N][32]; four points per 128-edge tile): the C5 stress shape of BASELINE.json */
+int lpd_edgeconv_dg32_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N,
+                          const void* w2, const float* s2, const float* t2, int act, float slope,
+                          void* x1, int ld1, void* x2, int ld2, void* stream);
 
 /* Fused input layers of the LPD-Net feature nets (lpdnet_model.py:231-232, :86-87), strict fp32, one pass:
  *     out[m][:] = act(s2 * (W2 . act(s1 * (W1 . x[m][0..D)) + t1)) + t2),   W1 [64][D], W2 [64][64], D <= 8

@@ -249,7 +249,16 @@ struct Dg20hParams {
     long long num_tiles;
 };
 
-__global__ void __launch_bounds__(D20_THREADS, 1)
+// KK = 20: 5 points x 24-row slots per 128-edge tile (the reference's k); KK = 32: 4 points x 32-row slots (the C5 stress shape)
+template <int KK>
+struct DgH {
+    static constexpr int SLOT = (KK + 7) / 8 * 8, PTS = 128 / SLOT, GROUP_WARPS = 2 * PTS, PROD_WARPS = 2 * GROUP_WARPS;
+    static constexpr int THREADS = 32 * (D20_EPI_WARPS + PROD_WARPS), ROWQ = KK / 4;
+    static_assert(KK % 4 == 0 && KK <= 32 && PTS * SLOT <= 128, "edge tile geometry");
+};
+
+template <int KK>
+__global__ void __launch_bounds__(DgH<KK>::THREADS, 1)
 edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -261,6 +270,7 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
     uint64_t* tfull = yempty + 2;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    constexpr int D20_K = KK, D20_SLOT = DgH<KK>::SLOT, D20_PTS = DgH<KK>::PTS, D20_GROUP_WARPS = DgH<KK>::GROUP_WARPS, D20_THREADS = DgH<KK>::THREADS, ROWQ = DgH<KK>::ROWQ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (uint32_t i = threadIdx.x; i < 2 * D20H_OP_BYTES / 16; i += D20_THREADS)
@@ -330,14 +340,14 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
                 const __half* pbase = P.p + (pt / P.N) * P.N * P.ldp + ch;
                 const __half2* qh = reinterpret_cast<const __half2*>(&qraw);
                 __half2 best[4] = {ninf, ninf, ninf, ninf};
-                uint4 pv[5];
+                uint4 pv[ROWQ];
 #pragma unroll
-                for (int i = 0; i < 5; ++i) {                                   // all 20 rows of the point in flight: 5 per lane
+                for (int i = 0; i < ROWQ; ++i) {                                // all rows of the point in flight: KK / 4 per lane
                     const int j = __shfl_sync(kFull, myj, 4 * i + sr);
                     pv[i] = __ldg(reinterpret_cast<const uint4*>(pbase + (unsigned)(j * P.ldp)));
                 }
 #pragma unroll
-                for (int i = 0; i < 5; ++i) {
+                for (int i = 0; i < ROWQ; ++i) {
                     const __half2* ph2 = reinterpret_cast<const __half2*>(&pv[i]);
                     uint4 y;
                     __half2* yh = reinterpret_cast<__half2*>(&y);
@@ -408,20 +418,27 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
                 const long long pt = t * D20_PTS + pl;
                 if (pt >= P.total_pts) break;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + s * D20_ACC_STRIDE + pl * D20_SLOT;
-                uint32_t r[20];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(taddr + 16));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t r[KK];
+                if constexpr (KK == 20) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(taddr + 16));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+                    uint32_t r32[32];
+                    tc_ld32(taddr, r32);
+#pragma unroll
+                    for (int u = 0; u < KK; ++u) r[u] = r32[u];
+                }
                 float a4[4], b4[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { a4[u] = __uint_as_float(r[u]); b4[u] = a4[u]; }
 #pragma unroll
-                for (int j = 4; j < 20; j += 2) {
+                for (int j = 4; j < KK; j += 2) {
                     const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
                     a4[(j >> 1) & 3] = fmaxf(fmaxf(a4[(j >> 1) & 3], v0), v1);
                     b4[(j >> 1) & 3] = fminf(fminf(b4[(j >> 1) & 3], v0), v1);
@@ -476,11 +493,11 @@ int dg20_tc_run(const float* p, int ldp, const float* q, int ldq, const int32_t*
 }  // namespace tc
 }  // namespace lpd
 
-extern "C" int lpd_edgeconv_dg20_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N,
-                                     const void* w2, const float* s2, const float* t2, int act, float slope,
-                                     void* x1, int ld1, void* x2, int ld2, void* stream) {
+static int edgeconv_dgk_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N, int K,
+                            const void* w2, const float* s2, const float* t2, int act, float slope,
+                            void* x1, int ld1, void* x2, int ld2, void* stream) {
     using namespace lpd;
-    LPD_REQUIRE(p && q && idx && w2 && s2 && t2 && x2 && B >= 1 && N >= 20);
+    LPD_REQUIRE(p && q && idx && w2 && s2 && t2 && x2 && B >= 1 && (K == 20 || K == 32) && N >= K);
     LPD_REQUIRE(ldp % 8 == 0 && ldq % 8 == 0 && ld2 % 2 == 0 && (!x1 || ld1 % 8 == 0));
     LPD_REQUIRE(ldp >= 128 && ldq >= 128 && ld2 >= 128 && (!x1 || ld1 >= 128));
     LPD_REQUIRE((long long)N * ldp < (1ll << 31));
@@ -496,7 +513,8 @@ extern "C" int lpd_edgeconv_dg20_f16(const void* p, int ldp, const void* q, int 
     P.x1 = reinterpret_cast<__half*>(x1); P.x2 = reinterpret_cast<__half*>(x2);
     P.ldp = ldp; P.ldq = ldq; P.ld1 = ld1; P.ld2 = ld2; P.total_pts = (long long)B * N; P.N = N;
     P.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
-    P.num_tiles = (P.total_pts + tc::D20_PTS - 1) / tc::D20_PTS;
+    const int pts = K == 32 ? tc::DgH<32>::PTS : tc::DgH<20>::PTS;
+    P.num_tiles = (P.total_pts + pts - 1) / pts;
     // W2 fp16 [128][128]: boxes of 64 halves x 128 rows, 128B swizzle
     tc::EncodeTiledFn enc = tc::get_encode();
     if (!enc) return LPD_ECUDA;
@@ -511,9 +529,26 @@ extern "C" int lpd_edgeconv_dg20_f16(const void* p, int ldp, const void* q, int 
         return LPD_ECUDA;
     }
     constexpr size_t smem = 3 * (size_t)tc::D20H_OP_BYTES + 256;
-    LPD_CUDA_CHECK(allow_smem(tc::edgeconv_dg20_h_kernel, smem));
     const int grid = (int)(P.num_tiles < sms ? P.num_tiles : sms);
-    tc::edgeconv_dg20_h_kernel<<<grid, tc::D20_THREADS, smem, as_stream(stream)>>>(tw, P);
+    if (K == 32) {
+        LPD_CUDA_CHECK(allow_smem(tc::edgeconv_dg20_h_kernel<32>, smem));
+        tc::edgeconv_dg20_h_kernel<32><<<grid, tc::DgH<32>::THREADS, smem, as_stream(stream)>>>(tw, P);
+    } else {
+        LPD_CUDA_CHECK(allow_smem(tc::edgeconv_dg20_h_kernel<20>, smem));
+        tc::edgeconv_dg20_h_kernel<20><<<grid, tc::DgH<20>::THREADS, smem, as_stream(stream)>>>(tw, P);
+    }
     LPD_LAUNCH_CHECK();
     return LPD_OK;
+}
+
+extern "C" int lpd_edgeconv_dg20_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N,
+                                     const void* w2, const float* s2, const float* t2, int act, float slope,
+                                     void* x1, int ld1, void* x2, int ld2, void* stream) {
+    return edgeconv_dgk_f16(p, ldp, q, ldq, idx, B, N, 20, w2, s2, t2, act, slope, x1, ld1, x2, ld2, stream);
+}
+
+extern "C" int lpd_edgeconv_dg32_f16(const void* p, int ldp, const void* q, int ldq, const int32_t* idx, int B, int N,
+                                     const void* w2, const float* s2, const float* t2, int act, float slope,
+                                     void* x1, int ld1, void* x2, int ld2, void* stream) {
+    return edgeconv_dgk_f16(p, ldp, q, ldq, idx, B, N, 32, w2, s2, t2, act, slope, x1, ld1, x2, ld2, stream);
 }

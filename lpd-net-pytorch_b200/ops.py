@@ -368,10 +368,14 @@ def edge_gather_max_f16(p, ldp, q, ldq, idx, B, N, k, C, act, slope, out, ldo):
 
 
 def edgeconv_dg20_f16(p, ldp, q, ldq, idx, B, N, w2_h, s2, t2, act, slope, x1, ld1, x2, ld2):
-    """the k = 20 / 128-channel double edge layer with fp16 rows in and out (lpd_edgeconv_dg20_f16)"""
+    """the 128-channel double edge layer with fp16 rows in and out, k = 20 or 32 taken from idx [B, N, k]
+    (lpd_edgeconv_dg20_f16 / lpd_edgeconv_dg32_f16)"""
     lib = _lib.load()
     _f16(p, "p"), _f16(w2_h, "w2")
-    _call("lpd_edgeconv_dg_f16[128x128]", 1, lib.lpd_edgeconv_dg20_f16, p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), B, N,
+    k = idx.shape[-1]
+    if k not in (20, 32):
+        raise _lib.LpdError(f"edgeconv_dg20_f16: k must be 20 or 32, got {k}")
+    _call("lpd_edgeconv_dg_f16[128x128]", 1, lib.lpd_edgeconv_dg20_f16 if k == 20 else lib.lpd_edgeconv_dg32_f16, p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), B, N,
           w2_h.data_ptr(), s2.data_ptr(), t2.data_ptr(), act, float(slope), _p(x1), ld1, x2.data_ptr(), ld2, _stream())
     return x1, x2
 

@@ -245,7 +245,7 @@ class LPDNet(_LPDBase):
     def forward_pm(self, x: torch.Tensor, keep_order: bool = False, f16: bool = False):
         """-> (F [B*N, emb] point-major, B, N).  Unless keep_order, the rows of every cloud are in spatial (grid-cell)
         order (ops.SPATIAL_ORDER): PointNetVlad feeds them to NetVLAD, which sums over the points.
-        f16 (PointNetVlad.forward in "f16" precision mode, k == 20): F and every activation downstream of the feature-space kNN
+        f16 (PointNetVlad.forward in "f16" precision mode, k == 20 or 32): F and every activation downstream of the feature-space kNN
         are fp16 tensors; conv1 / conv2 and both kNN graphs stay exact fp32."""
         require_cuda(x, "LPDNet")
         training_unsupported(self, "LPDNet")
@@ -255,7 +255,7 @@ class LPDNet(_LPDBase):
         act, slope = _act_code(self)
         dev = h.device
         idx_f = ops.knn(h.view(B, N, 64), k)
-        if f16 and k == 20 and M >= 128 and self.emb_dims % 4 == 0:
+        if f16 and k in (20, 32) and M >= 128 and self.emb_dims % 4 == 0:
             pq1 = ops.gemm_tf32_out16(h, p["wpq1"], M=M, N=256, K=64, scale=p["spq1"], shift=p["tpq1"])
             pyr = torch.empty(M, 512, device=dev, dtype=torch.float16)
             ops.edgeconv_dg20_f16(pq1, 256, pq1[:, 128:], 256, idx_f, B, N, p["wdg2_h"], p["sdg2"], p["tdg2"], act, slope,

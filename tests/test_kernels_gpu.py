@@ -575,13 +575,14 @@ def test_edge_gather_max_f16(cuda, B, N, k):
     assert np.array_equal(got[:, C:], want) and (got[:, :C] == 0).all()
 
 
-@pytest.mark.parametrize("B,N", [(2, 300), (1, 4096), (3, 1001), (1, 20)])
-def test_edgeconv_dg20_f16_kernel(cuda, B, N):
+@pytest.mark.parametrize("B,N,k", [(2, 300, 20), (1, 4096, 20), (3, 1001, 20), (1, 20, 20), (2, 300, 32), (1, 4099, 32), (1, 32, 32)])
+def test_edgeconv_dg20_f16_kernel(cuda, B, N, k):
     """edge_tc20.cu, fp16 form: y1 = fp16(leaky(p_j + q_i)) in half2 arithmetic, second layer fp16 x fp16 -> fp32 on tcgen05,
     x1 / x2 written as fp16.  Against float64 on the same fp16 inputs: x1 within one fp16 rounding of the exact value, x2 within
-    2^-9 of the layer-2 scale (fp16 rounding of y1, of the output, and of the slope constant on the negative branch)."""
-    k, C = 20, 128
-    r = rng(N + 78)
+    2^-9 of the layer-2 scale (fp16 rounding of y1, of the output, and of the slope constant on the negative branch).  k = 20 (five
+    points per 128-edge tile) and k = 32 (four)."""
+    C = 128
+    r = rng(N + 78 + k)
     pq = r.standard_normal((B * N, 2 * C)).astype(np.float16)
     idx = r.integers(0, N, (B, N, k)).astype(np.int32)
     s2, t2 = (r.standard_normal(C).astype(np.float32) for _ in range(2))

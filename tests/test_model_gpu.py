@@ -312,6 +312,25 @@ def test_f16_mode_descriptor_error_bound(cuda, golden, name, B, N, kw):
         assert err <= TF32_TOL, f"{name}: {err:.3e}"
 
 
+def test_f16_mode_k32_variant_matches_reference_golden(cuda, golden):
+    """the C5 neighbourhood size (k = 32) in f16 mode: the k = 32 form of the fp16 EdgeConv kernel runs, error inside the strict gate"""
+    g = golden("c5_lpdnet_k32_eval")
+    model, _ = build(g, num_points=2048, emb_dims=1024, featnet="lpdnet")
+    model.emb_nn.k = 32
+    prev = ops.set_precision("f16")
+    try:
+        ops.profile(True)
+        with torch.no_grad():
+            out = model(synth.clouds(1, 2048).cuda()).cpu().numpy()
+        labels = [l for l, _, _ in ops.profile(False)]
+    finally:
+        ops.set_precision(prev)
+    assert any(l.startswith("lpd_edgeconv_dg_f16[128x128]") for l in labels), labels
+    err = np.abs(out - g["out"]).max()
+    print(f"\n[f16] c5_lpdnet_k32_eval: max-abs descriptor error {err:.3e}")
+    assert err <= F16_TOL
+
+
 def test_f16_mode_through_the_embedding_driver(cuda, golden):
     """get_latent_vectors in f16 mode: graph replay == eager, and switching the precision mode re-captures the graph"""
     g = golden("c2_lpdnet_eval_small")
