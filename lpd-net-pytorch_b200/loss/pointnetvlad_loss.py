@@ -47,9 +47,18 @@ def best_pos_distance(query, pos_vecs):
     Bq, P, D = pos_vecs.shape
     if P > 32:
         raise NotImplementedError("best_pos_distance: at most 32 positives per query")
+    # one launch for all tuples: the positives of tuple b are database segment b of the exact per-segment search; the sorted [P]
+    # distance table of (query b, segment b) holds the minimum first and the maximum last
+    db = pos_vecs.detach().reshape(Bq * P, D)
+    q = query.detach().reshape(Bq, D)
+    if D % 4 == 0:
+        seg = torch.arange(0, (Bq + 1) * P, P, dtype=torch.int32, device=db.device)
+        _, dist = ops.retrieval_tc(db, q, P, seg)                                  # [segment, query, P], ascending
+        d = dist[torch.arange(Bq, device=db.device), torch.arange(Bq, device=db.device)]
+        return d[:, 0].float(), d[:, P - 1].float()
     mins, maxs = [], []
-    for b in range(Bq):  # a [P] table per tuple: the exact-search kernel returns its distances sorted ascending
-        _, d = ops.retrieval_topk(pos_vecs[b].detach(), query[b].detach().reshape(1, D), P)
+    for b in range(Bq):          # (descriptor sizes the tensor-core search does not take: one exact search per tuple)
+        _, d = ops.retrieval_topk(db[b * P:(b + 1) * P], q[b:b + 1], P)
         mins.append(d[0, 0])
         maxs.append(d[0, P - 1])
     return torch.stack(mins).float(), torch.stack(maxs).float()
