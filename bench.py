@@ -563,8 +563,10 @@ def bench_embed(ctx, tag: str):
     ranks = ctx.rank_report(per_step, clk.result)
 
     # ---- end to end through the public API: PINNED host clouds -> H2D -> descriptors -> D2H into host memory ----
-    big = torch.cat([h[:, 0] for h in host], 0).pin_memory()            # [4*B, N, 3]
-    reps = max(1, (ctx.steps + n_rot - 1) // n_rot)
+    # one call embeds 16 batches (1,024 submaps at C2: the size of one run of the reference's evaluation sets, evaluate.py:96-159)
+    e2e_batches = 4 * n_rot if tag == "c2" else n_rot
+    big = torch.cat([h[:, 0] for h in host] * (e2e_batches // n_rot), 0).pin_memory()   # [e2e_batches * B, N, 3]
+    reps = max(1, (ctx.steps + e2e_batches - 1) // e2e_batches)
     evaluate.get_latent_vectors(model, big, batch_num=B)                 # warm (stages buffers, captures the driver's own graph)
     te = ctx.timed_region(lambda: [evaluate.get_latent_vectors(model, big, batch_num=B) for _ in range(reps)])
     e2e_value = ctx.world * reps * big.shape[0] / (te * 1e-3)
@@ -607,7 +609,8 @@ def bench_embed(ctx, tag: str):
                "clocks": clk.result, "gpu_launches": launches,
                "per_rank_ms_per_step": [round(v / ctx.steps, 4) for v in per_rank], "ranks": ranks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N * 3 * 4, "d2h_bytes_per_step": B * 256 * 4,
-                       "api": "lpdnet_b200.evaluate.get_latent_vectors (pinned host clouds -> H2D -> graph replay -> D2H host descriptors)"},
+                       "api": "lpdnet_b200.evaluate.get_latent_vectors (pinned host clouds -> H2D -> graph replay -> D2H host descriptors)",
+                       "submaps_per_call": int(big.shape[0]), "calls": reps},
                "roofline": roofline_of(top, tot[top], cnt[top], step_ms, ctx.peaks, B, N, k), "rooflines": rooflines,
                "knn_netvlad": knn_netvlad, "families": fams, "kernel_breakdown": breakdown}
         if tag == "c2":

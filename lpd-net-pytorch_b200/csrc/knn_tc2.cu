@@ -254,20 +254,37 @@ __device__ __forceinline__ void knn2_fold_center(const float* __restrict__ part,
     __syncthreads();
 }
 
-// 0b. per point: fp16 centred operand row, both norms, per-cloud maxima
+// 0b. per point: fp16 centred operand row, both norms, per-cloud maxima.  One thread = one point (the canonical norm is a
+// sequential fmaf chain), but the 256-byte input rows and the 128-byte output rows of a block travel through shared memory so that
+// global memory only sees coalesced 16-byte accesses (a thread walking its own row touched 32 different lines per load instruction:
+// 0.043 ms for 100 MB).
+constexpr int K2_PREP_XS = 68;                         // staged input row stride in floats (conflict-free LDS.128 per thread)
+constexpr int K2_PREP_HS = 9;                          // staged output row stride in uint4
+constexpr size_t K2_PREP_SMEM = 256 * K2_PREP_XS * 4 + 256 * K2_PREP_HS * 16;
 __global__ void __launch_bounds__(256)
 knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, float* __restrict__ sc, int N, int Npad,
                  __half* __restrict__ xh, uint4* __restrict__ ext, float* __restrict__ xxpad, float* __restrict__ nrmpad,
                  float* __restrict__ snpad, float* __restrict__ r2, float* __restrict__ r2c) {
     __shared__ __align__(16) float mus_f[64];
     __shared__ float ssc[2], sred[64];
+    extern __shared__ __align__(16) uint8_t prep_sm[];
+    float* xs = reinterpret_cast<float*>(prep_sm);                               // [256][K2_PREP_XS]
+    uint4* hs = reinterpret_cast<uint4*>(prep_sm + 256 * K2_PREP_XS * 4);        // [256][K2_PREP_HS], row = storage position
     const int b = blockIdx.y;
-    knn2_fold_center(part, b, N, mus_f, ssc, sred);
+    const int n0 = blockIdx.x * 256;
+    // the block's input rows, coalesced (in flight while the centre is folded)
+    {
+        const float4* src = reinterpret_cast<const float4*>(x + ((size_t)b * N + n0) * 64);
+        const int rows = min(256, N - n0);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < rows * 16; i += 256)
+            *reinterpret_cast<float4*>(xs + (i >> 4) * K2_PREP_XS + (i & 15) * 4) = __ldg(src + i);
+    }
+    knn2_fold_center(part, b, N, mus_f, ssc, sred);                               // (ends with __syncthreads)
     const float4* mus = reinterpret_cast<const float4*>(mus_f);
     const float sigma = ssc[0];
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc[2 * b] = sigma; sc[2 * b + 1] = ssc[1]; }
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= Npad) return;
+    const int n = n0 + threadIdx.x;
     float vxx = INFINITY, vn = INFINITY;
     int np = n;                                   // storage position of point n (scrambled inside full 64-blocks)
     if ((n | 63) < N) {
@@ -276,12 +293,12 @@ knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, fl
         np = (n & ~63) | (((n & 63) * a + bb) & 63);
     }
     if (n < N) {
-        const float4* p = reinterpret_cast<const float4*>(x + ((size_t)b * N + n) * 64);
-        uint4* o = reinterpret_cast<uint4*>(xh + ((size_t)b * N + np) * 64);
+        const float4* p = reinterpret_cast<const float4*>(xs + threadIdx.x * K2_PREP_XS);
+        uint4* o = hs + (np - n0) * K2_PREP_HS;
         float acc = 0.f, accc = 0.f;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-            const float4 t0 = __ldg(p + 2 * g), t1 = __ldg(p + 2 * g + 1);
+            const float4 t0 = p[2 * g], t1 = p[2 * g + 1];
             acc = __fmaf_rn(t0.x, t0.x, acc); acc = __fmaf_rn(t0.y, t0.y, acc);
             acc = __fmaf_rn(t0.z, t0.z, acc); acc = __fmaf_rn(t0.w, t0.w, acc);
             acc = __fmaf_rn(t1.x, t1.x, acc); acc = __fmaf_rn(t1.y, t1.y, acc);
@@ -301,6 +318,13 @@ knn2_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, fl
         vxx = acc; vn = accc;
         atomicMax(reinterpret_cast<int*>(r2 + b), __float_as_int(acc));     // >= 0 (or NaN bits, harmless): int order == float order
         atomicMax(reinterpret_cast<int*>(r2c + b), __float_as_int(accc));
+    }
+    __syncthreads();
+    {   // the block's operand rows in storage order, coalesced
+        uint4* dst = reinterpret_cast<uint4*>(xh + ((size_t)b * N + n0) * 64);
+        const int rows = min(256, N - n0);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < rows * 8; i += 256) dst[i] = hs[(i >> 3) * K2_PREP_HS + (i & 7)];
     }
     // K-extension row of the candidate operand: the tensor core itself subtracts V = sigma^2 nrm / 2 from the gram entry,
     //   t_ij = sigma^2 x'_i.x'_j - V_j = (sigma^2 / 2) a_ij,   V = 2^6 B1 + 2^-5 B2 + 2^-14 B3  (three fp16 pieces, residual
@@ -1145,7 +1169,9 @@ int knn2_run(const float* x, int B, int N, int k, void* idx, int idx_i64, void* 
     LPD_CUDA_CHECK(cudaMemsetAsync(flags, 0, W.off_list - W.off_flags + sizeof(int), st));   // the flags and the list length
     knn2_center_kernel<<<dim3(K2_CSPLIT, B), 256, 0, st>>>(x, N, mu);
     LPD_LAUNCH_CHECK();
-    knn2_prep_kernel<<<dim3(ceil_div(W.npad, 256), B), 256, 0, st>>>(x, mu, sc, N, W.npad, xh, reinterpret_cast<uint4*>(ws + W.off_ext), xxpad, nrmpad, snpad, r2, r2c);
+    static bool prep_smem_ok = false;
+    if (!prep_smem_ok) { LPD_CUDA_CHECK(allow_smem(knn2_prep_kernel, K2_PREP_SMEM)); prep_smem_ok = true; }
+    knn2_prep_kernel<<<dim3(ceil_div(W.npad, 256), B), 256, K2_PREP_SMEM, st>>>(x, mu, sc, N, W.npad, xh, reinterpret_cast<uint4*>(ws + W.off_ext), xxpad, nrmpad, snpad, r2, r2c);
     LPD_LAUNCH_CHECK();
     CUtensorMap ta, tb;
     int rc = make_tmap_f16(&ta, xh, (long long)B * N, 128);
