@@ -450,6 +450,7 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
+    __syncthreads();                                       // (the CTA-level barrier is what racecheck models; the cluster barrier orders the pair)
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
