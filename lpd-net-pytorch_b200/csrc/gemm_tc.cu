@@ -366,8 +366,9 @@ static int make_tmap_h(CUtensorMap* m, const void* base, long long rows, int col
 // lines).  Per SM: 64 B/clk operand reads + 64 B/clk TMA + 32 B/clk staging.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int H2_STAGES = 5;
+constexpr int H2_MAXN = 2048;                           // columns whose epilogue scale / shift are kept in shared memory
 constexpr uint32_t H2_A_BYTES = 128 * 128, H2_B_BYTES = 128 * 128, H2_STAGE_BYTES = H2_A_BYTES + H2_B_BYTES;
-constexpr size_t H2_SMEM = (size_t)H2_STAGES * H2_STAGE_BYTES + EPI_WARPS * 32 * 128 + 256;
+constexpr size_t H2_SMEM = (size_t)H2_STAGES * H2_STAGE_BYTES + EPI_WARPS * 32 * 128 + 2 * H2_MAXN * 4 + 256;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -423,13 +424,19 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* cstage = smem + H2_STAGES * H2_STAGE_BYTES;                             // [EPI_WARPS][32 rows][128 B]
-    uint64_t* full = reinterpret_cast<uint64_t*>(cstage + EPI_WARPS * 32 * 128);
+    float* ssc = reinterpret_cast<float*>(cstage + EPI_WARPS * 32 * 128);            // [H2_MAXN] epilogue scale, then shift
+    float* ssh = ssc + H2_MAXN;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ssh + H2_MAXN);
     uint64_t* empty = full + H2_STAGES;
     uint64_t* tfull = empty + H2_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < p.N; i += THREADS) {     // (made visible by the barriers below)
+        ssc[i] = p.scale ? __ldg(p.scale + i) : 1.f;
+        ssh[i] = p.shift ? __ldg(p.shift + i) : 0.f;
+    }
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     constexpr bool HALF = sizeof(TIN) == 2;
@@ -518,9 +525,7 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int col = col0 + h * 32 + 4 * j;
-                        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
-                        if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+                        const float4 sc = *reinterpret_cast<const float4*>(ssc + col), sh = *reinterpret_cast<const float4*>(ssh + col);   // warp broadcast
                         float v0 = fmaf(__uint_as_float(r[4 * j]), sc.x, sh.x), v1 = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
                         float v2 = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
                         v0 = fmaxf(v0, v0 * p.neg_slope); v1 = fmaxf(v1, v1 * p.neg_slope);
@@ -546,7 +551,7 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) {                               // the accumulator stage is free again: tell the leader's MMA warp
                 const uint32_t lbar = mapa_u32(smem_u32(&tempty[acc]), 0);
-                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
+                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -691,7 +696,7 @@ extern "C" int lpd_gemm_f16(const void* A, int lda, const void* W, int ldw, void
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
     p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
-    if (out_half && (N % 256) == 0 && (ldc % 8) == 0 && g_gemm_2cta) {                // CTA-pair kernel (cta_group::2)
+    if (out_half && (N % 256) == 0 && N <= tc::H2_MAXN && (ldc % 8) == 0 && g_gemm_2cta) {   // CTA-pair kernel (cta_group::2)
         rc = tc::make_tmap_h(&tb, W, N, K, ldw, 128);                                  // each CTA loads 128 of the tile's 256 rows of W
         if (rc != LPD_OK) return rc;
         return tc::launch_h2<__half>(ta, tb, p, st);
@@ -790,7 +795,7 @@ extern "C" int lpd_gemm_tf32_out16(const float* A, int lda, const float* B, int 
     p.neg_slope = act == LPD_ACT_NONE ? 1.f : (act == LPD_ACT_RELU ? 0.f : slope);
     p.tiles_m = p.tiles_n = 0; p.batch = 1; p.strideC = 0; p.bM = p.bN = 0; p.accumulate = 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
-    if ((N % 256) == 0 && (ldc % 8) == 0 && g_gemm_2cta) {                             // CTA-pair kernel (cta_group::2)
+    if ((N % 256) == 0 && N <= tc::H2_MAXN && (ldc % 8) == 0 && g_gemm_2cta) {         // CTA-pair kernel (cta_group::2)
         rc = tc::make_tmap(&tb, B, N, K, ldb, 128);
         if (rc != LPD_OK) return rc;
         return tc::launch_h2<float>(ta, tb, p, st);
