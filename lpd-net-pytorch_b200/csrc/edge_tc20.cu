@@ -336,6 +336,8 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
             const long long pt = t * D20_PTS + pl;
             prefetch(t + tstep);
             mbar_wait(&yempty[grp], ph ^ 1);
+            uint4 x1v = make_uint4(0u, 0u, 0u, 0u);
+            bool x1ok = false;
             if (pt < P.total_pts) {
                 const __half* pbase = P.p + (pt / P.N) * P.N * P.ldp + ch;
                 const __half2* qh = reinterpret_cast<const __half2*>(&qraw);
@@ -373,12 +375,15 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
                         const __half2 z = __hadd2(m2, qh[v]);                   // max_m act(p'_m + q') = act(max_m p'_m + q')
                         oh[v] = __hmax2(z, __hmul2(z, slope2));
                     }
-                    if (sr == 0) *reinterpret_cast<uint4*>(P.x1 + pt * P.ld1 + ch) = o;
+                    x1v = o; x1ok = sr == 0;
                 }
             }
+            // (the proxy fence compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it waits for every memory operation of the thread that
+            // is still in flight, so the x1 store goes AFTER it instead of sitting in front of the operand hand-over)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&yfull[grp]);
+            if (x1ok) *reinterpret_cast<uint4*>(P.x1 + pt * P.ld1 + ch) = x1v;
             if (issuer) {
                 if (!w_ready) { mbar_wait(wfull, 0); w_ready = true; }
                 mbar_wait(&tempty[grp], ph ^ 1);
