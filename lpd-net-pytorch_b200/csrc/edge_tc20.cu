@@ -334,20 +334,24 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
             const int myj = nj;
             const uint4 qraw = nq;
             const long long pt = t * D20_PTS + pl;
-            prefetch(t + tstep);
-            mbar_wait(&yempty[grp], ph ^ 1);
-            uint4 x1v = make_uint4(0u, 0u, 0u, 0u);
-            bool x1ok = false;
+            // the neighbour rows of this tile are requested BEFORE the wait for the operand stage (the MMA of the group's previous
+            // tile is still reading it): the gather latency runs under that MMA instead of after it
+            uint4 pv[ROWQ];
             if (pt < P.total_pts) {
                 const __half* pbase = P.p + (pt / P.N) * P.N * P.ldp + ch;
-                const __half2* qh = reinterpret_cast<const __half2*>(&qraw);
-                __half2 best[4] = {ninf, ninf, ninf, ninf};
-                uint4 pv[ROWQ];
 #pragma unroll
                 for (int i = 0; i < ROWQ; ++i) {                                // all rows of the point in flight: KK / 4 per lane
                     const int j = __shfl_sync(kFull, myj, 4 * i + sr);
                     pv[i] = __ldg(reinterpret_cast<const uint4*>(pbase + (unsigned)(j * P.ldp)));
                 }
+            }
+            prefetch(t + tstep);
+            mbar_wait(&yempty[grp], ph ^ 1);
+            uint4 x1v = make_uint4(0u, 0u, 0u, 0u);
+            bool x1ok = false;
+            if (pt < P.total_pts) {
+                const __half2* qh = reinterpret_cast<const __half2*>(&qraw);
+                __half2 best[4] = {ninf, ninf, ninf, ninf};
 #pragma unroll
                 for (int i = 0; i < ROWQ; ++i) {
                     const __half2* ph2 = reinterpret_cast<const __half2*>(&pv[i]);
@@ -418,12 +422,13 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
             mbar_wait(&tfull[s], ph);
             tc_fence_after();
-#pragma unroll 1
-            for (int pl = 0; pl < D20_PTS; ++pl) {
-                const long long pt = t * D20_PTS + pl;
-                if (pt >= P.total_pts) break;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + s * D20_ACC_STRIDE + pl * D20_SLOT;
-                uint32_t r[KK];
+            // The accumulator columns of point pl + 1 are requested before point pl is reduced (a tcgen05.ld + wait per point left
+            // the four epilogue warps ~1900 clk per tile, more than the producers need: ncu showed the producers spinning on the
+            // operand stage for 18 % of their samples), and the accumulator stage is handed back as soon as the last point's
+            // columns are in registers.
+            const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + s * D20_ACC_STRIDE;
+            auto request = [&](int pl, uint32_t (&r)[KK]) {
+                const uint32_t taddr = tbase + pl * D20_SLOT;
                 if constexpr (KK == 20) {
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -432,13 +437,21 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
                         : "r"(taddr));
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                                  : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(taddr + 16));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 } else {
-                    uint32_t r32[32];
-                    tc_ld32(taddr, r32);
-#pragma unroll
-                    for (int u = 0; u < KK; ++u) r[u] = r32[u];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
                 }
+            };
+            auto reduce_store = [&](int pl, const uint32_t (&r)[KK]) {
+                const long long pt = t * D20_PTS + pl;
+                if (pt >= P.total_pts) return;
                 float a4[4], b4[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { a4[u] = __uint_as_float(r[u]); b4[u] = a4[u]; }
@@ -459,10 +472,22 @@ edgeconv_dg20_h_kernel(const __grid_constant__ CUtensorMap tmap_w2, Dg20hParams 
                     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(*reinterpret_cast<uint32_t*>(&h)) : "f"(vn), "f"(v));
                     *reinterpret_cast<__half2*>(P.x2 + pt * P.ld2 + ch) = h;
                 }
+            };
+            uint32_t ra[KK], rb[KK];
+            request(0, ra);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int pl = 0; pl < D20_PTS; ++pl) {
+                const bool more = pl + 1 < D20_PTS;
+                if (more) { if (pl & 1) request(pl + 1, ra); else request(pl + 1, rb); }
+                else {                                         // every column of the stage is in registers: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[s]);
+                }
+                if (pl & 1) reduce_store(pl, rb); else reduce_store(pl, ra);
+                if (more) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[s]);
         }
     }
     tc_fence_before();
