@@ -418,7 +418,8 @@ __device__ __forceinline__ void tc_mma_tf32_2sm_e(uint32_t tmem_d, uint64_t desc
 }
 
 // TIN = __half: fp16 operands (kind::f16, 64 K elements per 128-byte row); TIN = float: fp32 operands consumed as TF32 (32 per row)
-template <typename TIN>
+// OUT32: fp32 output (the training path's plain conv / dgrad GEMMs); else fp16
+template <typename TIN, bool OUT32 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -513,6 +514,34 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const int row0 = m0 + q * 32;
+            if constexpr (OUT32) {
+                // fp32 output: four chunks of 32 columns (128 bytes per row), raw accumulators staged like the single-CTA kernel
+                float* stgf = reinterpret_cast<float*>(stg);
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) {
+                    const int c32 = half * 4 + i, col0 = n0 + c32 * 32;
+                    if (row0 >= p.M) break;                 // warp-uniform
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c32 * 32, r);
+                    float* dst = stgf + lane * 32;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    __syncwarp();
+                    const int col = col0 + ch * 4;
+                    const float4 sc = *reinterpret_cast<const float4*>(ssc + col), sh = *reinterpret_cast<const float4*>(ssh + col);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + rsub;
+                        float4 v = *reinterpret_cast<const float4*>(stgf + rr * 32 + ((ch ^ (rr & 7)) << 2));
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        v.x = fmaxf(v.x, v.x * p.neg_slope); v.y = fmaxf(v.y, v.y * p.neg_slope);
+                        v.z = fmaxf(v.z, v.z * p.neg_slope); v.w = fmaxf(v.w, v.w * p.neg_slope);
+                        if (row0 + rr < p.M) *reinterpret_cast<float4*>(p.C + (size_t)(row0 + rr) * p.ldc + col) = v;
+                    }
+                    __syncwarp();
+                }
+            } else
 #pragma unroll 1
             for (int i = 0; i < 2; ++i) {
                 const int c64 = half * 2 + i, col0 = n0 + c64 * 64;
@@ -564,9 +593,9 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
-template <typename TIN>
+template <typename TIN, bool OUT32 = false>
 static int launch_h2(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
-    LPD_CUDA_CHECK(allow_smem(gemm_h2_kernel<TIN>, H2_SMEM));
+    LPD_CUDA_CHECK(allow_smem(gemm_h2_kernel<TIN, OUT32>, H2_SMEM));
     int dev = 0, sms = 0;
     LPD_CUDA_CHECK(cudaGetDevice(&dev));
     LPD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -575,7 +604,7 @@ static int launch_h2(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cud
     const long long tiles = (long long)p.tiles_m * p.tiles_n;
     const long long pairs = sms / 2;
     const int grid = (int)(2 * (tiles < pairs ? tiles : pairs));
-    gemm_h2_kernel<TIN><<<grid, THREADS, H2_SMEM, st>>>(ta, tb, p);
+    gemm_h2_kernel<TIN, OUT32><<<grid, THREADS, H2_SMEM, st>>>(ta, tb, p);
     LPD_LAUNCH_CHECK();
     return LPD_OK;
 }
@@ -767,6 +796,11 @@ extern "C" int lpd_gemm_tf32_ex(const float* A, int lda, const float* B, int ldb
     p.tiles_m = p.tiles_n = 0; p.batch = batch; p.strideC = 0;
     p.bM = batch > 1 ? M : 0; p.bN = batch > 1 ? N : 0; p.accumulate = accumulate ? 1 : 0; p.a_h = nullptr; p.apart = nullptr;
     cudaStream_t st = as_stream(stream);
+    if (batch == 1 && !accumulate && (N % 256) == 0 && N <= tc::H2_MAXN && M >= 1024 && g_gemm_2cta) {   // CTA-pair kernel, fp32 output
+        rc = tc::make_tmap(&tb, B, N, K, ldb, 128);
+        if (rc != LPD_OK) return rc;
+        return tc::launch_h2<float, true>(ta, tb, p, st);
+    }
     if (BN == 64) return tc::launch<64, 8>(ta, tb, p, st);
     if (BN == 128) return tc::launch<128, 6>(ta, tb, p, st);
     return tc::launch<256, 4>(ta, tb, p, st);

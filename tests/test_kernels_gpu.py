@@ -439,7 +439,7 @@ def test_pointwise_mlp2_matches_two_fp32_layers(cuda, M, D, ld, act):
 
 # ------------------------------------------------------------------------------------------------ tensor-core GEMM
 @pytest.mark.parametrize("M,N,K,ldx", [(1000, 1024, 512, 0), (128, 64, 1024, 0), (300, 512, 128, 0), (4096, 256, 64, 0),
-                                       (777, 200, 96, 0), (2048, 128, 128, 512), (130, 1024, 40, 0)])
+                                       (777, 200, 96, 0), (2048, 128, 128, 512), (130, 1024, 40, 0), (40000, 1024, 512, 0), (5001, 512, 100, 0)])
 def test_gemm_tf32_tensor_core_path(cuda, M, N, K, ldx):
     """tcgen05 kind::tf32: operands are rounded to TF32 (10-bit mantissa) -> tolerance 2^-9 of the result scale."""
     r = rng(M + N + K)
